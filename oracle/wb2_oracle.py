@@ -1,0 +1,687 @@
+"""CPU oracle for the WeatherBench2 hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module is a NumPy restatement of the reference algorithms named in
+SURVEY.md section 8 (metrics / regions / conservative regridder / zonal energy
+spectrum).  It is the *checker*: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.
+The product package (``weatherbench2_b200``) never imports anything from
+``oracle/``; its numerical path is the CUDA library behind the C ABI in
+``include/wb2b200.h`` and it fails loudly when that library is missing.
+
+Parity status: **pinned** against every known-answer value the reference's own
+tests hold for this path (``tests/test_oracle_golden.py`` lists them with the
+reference test file:line).  The reference itself cannot be imported in this
+container or on the GPU box (it needs xarray / jax / apache_beam, none of which
+are installed and there is no network), so the oracle restates, operation for
+operation, what xarray (>=2024.11), NumPy (>=2.1) and JAX do underneath the
+reference's calls.  Each function cites the reference lines it follows
+(paths relative to ``/root/reference``).
+
+Everything works on plain ``numpy`` arrays plus a tuple of dimension names
+(``dims``), i.e. the information an ``xarray.DataArray`` carries.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional, Sequence, Union
+
+import numpy as np
+
+EARTH_RADIUS_M = 1000 * (6357 + 6378) / 2  # weatherbench2/schema.py:59
+
+LAT = "latitude"
+LON = "longitude"
+
+
+# ----------------------------------------------------------------------------
+# Latitude weights -- weatherbench2/metrics.py:35-60
+# ----------------------------------------------------------------------------
+def _assert_increasing(x: np.ndarray):
+  # metrics.py:35-37
+  if not (np.diff(x) > 0).all():
+    raise ValueError(f"array is not increasing: {x}")
+
+
+def _latitude_cell_bounds(x: np.ndarray) -> np.ndarray:
+  # metrics.py:40-42 (radians; keeps x.dtype)
+  pi_over_2 = np.array([np.pi / 2], dtype=x.dtype)
+  return np.concatenate([-pi_over_2, (x[:-1] + x[1:]) / 2, pi_over_2])
+
+
+def _cell_area_from_latitude(points: np.ndarray) -> np.ndarray:
+  # metrics.py:45-52
+  bounds = _latitude_cell_bounds(points)
+  _assert_increasing(bounds)
+  upper = bounds[1:]
+  lower = bounds[:-1]
+  return np.sin(upper) - np.sin(lower)
+
+
+def get_lat_weights(latitude: np.ndarray) -> np.ndarray:
+  """metrics.py:55-60.  `latitude` in degrees, strictly increasing."""
+  weights = _cell_area_from_latitude(np.deg2rad(np.asarray(latitude)))
+  weights = weights / np.mean(weights)
+  return weights
+
+
+# ----------------------------------------------------------------------------
+# Regions -- weatherbench2/regions.py:40-158
+# ----------------------------------------------------------------------------
+def _label_slice_indices(coord: np.ndarray, s: slice) -> np.ndarray:
+  """Indices selected by ``.sel(dim=slice(lo, hi))`` on a monotonic increasing
+  float index (pandas `Index.slice_indexer`: both ends inclusive; labels need
+  not be present).  regions.py:79-84 rely on this rule."""
+  coord = np.asarray(coord)
+  if s.step is not None:
+    raise ValueError("slice steps are not used by the reference")
+  start = 0 if s.start is None else int(np.searchsorted(coord, s.start, "left"))
+  stop = (
+      coord.size if s.stop is None
+      else int(np.searchsorted(coord, s.stop, "right"))
+  )
+  return np.arange(start, max(start, stop))
+
+
+@dataclasses.dataclass
+class SliceRegion:
+  """regions.py:57-95."""
+  lat_slice: Union[slice, list] = dataclasses.field(
+      default_factory=lambda: slice(None, None))
+  lon_slice: Union[slice, list] = dataclasses.field(
+      default_factory=lambda: slice(None, None))
+
+
+@dataclasses.dataclass
+class ExtraTropicalRegion:
+  """regions.py:98-109 (note the hard-coded 20 at :108)."""
+  threshold_lat: Optional[float] = 20
+
+
+@dataclasses.dataclass
+class LandRegion:
+  """regions.py:112-138.  `land_sea_mask` has dims (latitude, longitude)."""
+  land_sea_mask: np.ndarray
+  threshold: Optional[float] = None
+
+
+@dataclasses.dataclass
+class CombinedRegion:
+  """regions.py:141-158."""
+  regions: list = dataclasses.field(default_factory=list)
+
+
+def _region_apply(region, x, w, lat, lon):
+  """Region.apply on data `x` (..., lat, lon) with 2-D weights `w` (lat, lon).
+
+  Returns (x, w, lat, lon) after the region (regions.py:40-158).  Weights are
+  carried as a dense (lat, lon) array, which is what xarray broadcasting
+  produces inside `weighted().mean` anyway.
+  """
+  if isinstance(region, SliceRegion):
+    lats = region.lat_slice if isinstance(region.lat_slice, list) else [
+        region.lat_slice]
+    lons = region.lon_slice if isinstance(region.lon_slice, list) else [
+        region.lon_slice]
+    # regions.py:79-84: concat of label slices (no dedup)
+    ilat = np.concatenate([_label_slice_indices(lat, s) for s in lats])
+    ilon = np.concatenate([_label_slice_indices(lon, s) for s in lons])
+    x = x[..., ilat, :][..., :, ilon]
+    w = w[ilat, :][:, ilon]
+    return x, w, lat[ilat], lon[ilon]
+  if isinstance(region, ExtraTropicalRegion):
+    region_weights = (np.abs(lat) >= 20).astype(float)  # regions.py:108
+    return x, w * region_weights[:, None], lat, lon
+  if isinstance(region, LandRegion):
+    land = np.asarray(region.land_sea_mask)
+    if land.shape != (lat.size, lon.size):
+      raise ValueError("oracle LandRegion needs a full (lat, lon) mask")
+    if region.threshold is not None:
+      land = (land > region.threshold).astype(float)  # regions.py:136-137
+    return x, w * land, lat, lon
+  if isinstance(region, CombinedRegion):
+    for r in region.regions:  # regions.py:155-157
+      x, w, lat, lon = _region_apply(r, x, w, lat, lon)
+    return x, w, lat, lon
+  raise TypeError(f"unknown region {region!r}")
+
+
+# ----------------------------------------------------------------------------
+# Weighted spatial mean -- metrics.py:141-172 + xarray Weighted._weighted_mean
+# ----------------------------------------------------------------------------
+def _to_lat_lon_last(x: np.ndarray, dims: Sequence[str]):
+  dims = tuple(dims)
+  ilat, ilon = dims.index(LAT), dims.index(LON)
+  rest = [i for i in range(len(dims)) if i not in (ilat, ilon)]
+  xt = np.transpose(x, rest + [ilat, ilon])
+  return xt, tuple(dims[i] for i in rest)
+
+
+def spatial_average(x, dims, lat, lon, region=None, skipna=False):
+  """metrics.py:141-163.  Returns (result, out_dims); result is float64.
+
+  xarray semantics restated (xarray/core/weighted.py `_weighted_mean`,
+  `_sum_of_weights`, `_reduce`):
+    sum  = dot(x.fillna(0) if skipna else x, w)
+    sow  = dot(notnull(x), w)          # ALWAYS masked; sow == 0 -> NaN
+    mean = sum / sow
+  """
+  lat = np.asarray(lat)
+  lon = np.asarray(lon)
+  xt, out_dims = _to_lat_lon_last(np.asarray(x), dims)
+  w = np.broadcast_to(get_lat_weights(lat)[:, None], (lat.size, lon.size))
+  if region is not None:
+    xt, w, lat, lon = _region_apply(region, xt, w, lat, lon)
+    xt = np.where(w > 0, xt, 0)  # metrics.py:160
+  mask = ~np.isnan(xt)
+  xs = np.where(mask, xt, 0) if skipna else xt
+  with np.errstate(invalid="ignore", over="ignore"):
+    num = np.einsum("...ij,ij->...", xs.astype(np.float64), w)
+    den = np.einsum("...ij,ij->...", mask.astype(np.float64), w)
+  den = np.where(den != 0.0, den, np.nan)
+  with np.errstate(invalid="ignore", divide="ignore"):
+    return num / den, out_dims
+
+
+def spatial_average_l2_norm(x, dims, lat, lon, region=None, skipna=False):
+  # metrics.py:166-172
+  r, d = spatial_average(np.asarray(x) ** 2, dims, lat, lon, region, skipna)
+  with np.errstate(invalid="ignore"):
+    return np.sqrt(r), d
+
+
+# ----------------------------------------------------------------------------
+# Named-dim broadcasting (what xarray arithmetic does between two operands)
+# ----------------------------------------------------------------------------
+def align(a, adims, b, bdims):
+  """Broadcast two named arrays against each other (xarray rule: result dims =
+  dims of `a` in order, then dims only in `b`)."""
+  adims, bdims = tuple(adims), tuple(bdims)
+  out = list(adims) + [d for d in bdims if d not in adims]
+
+  def expand(x, xd):
+    x = np.asarray(x)
+    perm = [xd.index(d) for d in out if d in xd]
+    x = np.transpose(x, perm)
+    shape = [slice(None) if d in xd else None for d in out]
+    return x[tuple(shape)]
+
+  return expand(a, adims), expand(b, bdims), tuple(out)
+
+
+def time_mean(x, dims, skipna=False, avg_dim=None):
+  """Metric.compute's `.mean(avg_dim, skipna=skipna)` -- metrics.py:117-138."""
+  dims = tuple(dims)
+  if avg_dim is None:
+    avg_dim = "time" if "time" in dims else "init_time"
+  ax = dims.index(avg_dim)
+  with np.errstate(invalid="ignore"):
+    import warnings
+    with warnings.catch_warnings():
+      warnings.simplefilter("ignore", RuntimeWarning)
+      r = np.nanmean(x, axis=ax) if skipna else np.mean(x, axis=ax)
+  return r, tuple(d for d in dims if d != avg_dim)
+
+
+# ----------------------------------------------------------------------------
+# Deterministic metrics -- metrics.py:175-414
+# ----------------------------------------------------------------------------
+def mse(f, fdims, t, tdims, lat, lon, region=None, skipna=False):
+  # metrics.py:283-292
+  fa, ta, d = align(f, fdims, t, tdims)
+  return spatial_average((fa - ta) ** 2, d, lat, lon, region, skipna)
+
+
+def rmse_sqrt_before_time_avg(f, fdims, t, tdims, lat, lon, region=None,
+                              skipna=False):
+  # metrics.py:251-260
+  fa, ta, d = align(f, fdims, t, tdims)
+  return spatial_average_l2_norm(fa - ta, d, lat, lon, region, skipna)
+
+
+def mae(f, fdims, t, tdims, lat, lon, region=None, skipna=False):
+  # metrics.py:323-330
+  fa, ta, d = align(f, fdims, t, tdims)
+  return spatial_average(np.abs(fa - ta), d, lat, lon, region, skipna)
+
+
+def bias(f, fdims, t, tdims, lat, lon, region=None, skipna=False):
+  # metrics.py:352-359
+  fa, ta, d = align(f, fdims, t, tdims)
+  return spatial_average(fa - ta, d, lat, lon, region, skipna)
+
+
+def wind_vector_mse(fu, fv, fdims, tu, tv, tdims, lat, lon, region=None,
+                    skipna=False):
+  # metrics.py:189-202
+  fua, tua, d = align(fu, fdims, tu, tdims)
+  fva, tva, _ = align(fv, fdims, tv, tdims)
+  du, dv = fua - tua, fva - tva
+  return spatial_average(du ** 2 + dv ** 2, d, lat, lon, region, skipna)
+
+
+def acc(f, fdims, t, tdims, c, cdims, lat, lon, region=None, skipna=False):
+  """metrics.py:387-414.  `c` is the climatology ALREADY selected onto the
+  forecast's (valid) times and levels (metrics.py:398-404 is label lookup)."""
+  fa, ca, d1 = align(f, fdims, c, cdims)
+  f_anom = fa - ca
+  ta, ca2, d2 = align(t, tdims, c, cdims)
+  t_anom = ta - ca2
+  fa2, ta2, d = align(f_anom, d1, t_anom, d2)
+  num, od = spatial_average(fa2 * ta2, d, lat, lon, region, skipna)
+  ff, _ = spatial_average(f_anom ** 2, d1, lat, lon, region, skipna)
+  tt, od2 = spatial_average(t_anom ** 2, d2, lat, lon, region, skipna)
+  od1 = tuple(x for x in d1 if x not in (LAT, LON))
+  ffa, tta, odp = align(ff, od1, tt, od2)
+  numa, dena, odf = align(num, od, ffa * tta, odp)
+  with np.errstate(invalid="ignore", divide="ignore"):
+    return numa / np.sqrt(dena), odf
+
+
+# ----------------------------------------------------------------------------
+# Ensemble metrics -- metrics.py:532-846, 1161-1517
+# ----------------------------------------------------------------------------
+def _mean(x, axis, skipna):
+  import warnings
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore", RuntimeWarning)
+    with np.errstate(invalid="ignore"):
+      return np.nanmean(x, axis=axis) if skipna else np.mean(x, axis=axis)
+
+
+def _var(x, axis, skipna, ddof=1):
+  import warnings
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore", RuntimeWarning)
+    with np.errstate(invalid="ignore", divide="ignore"):
+      if skipna:
+        return np.nanvar(x, axis=axis, ddof=ddof)
+      return np.var(x, axis=axis, ddof=ddof)
+
+
+def rankdata(x: np.ndarray, axis: int) -> np.ndarray:
+  """metrics.py:836-846 (ordinal ranks; NaN sorts last, np.argsort default)."""
+  x = np.asarray(x)
+  x = np.swapaxes(x, axis, -1)
+  j = np.argsort(x, axis=-1)
+  ordinal_ranks = np.broadcast_to(
+      np.arange(1, x.shape[-1] + 1, dtype=int), x.shape)
+  ordered_ranks = np.empty(j.shape, dtype=ordinal_ranks.dtype)
+  np.put_along_axis(ordered_ranks, j, ordinal_ranks, axis=-1)
+  return np.swapaxes(ordered_ranks, axis, -1)
+
+
+def pointwise_crps_spread(f, fdims, ens_dim, skipna):
+  # metrics.py:781-813
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  n = f.shape[ax]
+  od = tuple(d for d in fdims if d != ens_dim)
+  if n < 2:
+    return np.zeros_like(np.take(f, 0, axis=ax)), od  # :788-789
+  rank = rankdata(f, ax)
+  return 2 * _mean((2 * rank - n - 1) * f, ax, skipna) / (n - 1), od
+
+
+def pointwise_crps_skill(f, fdims, t, tdims, ens_dim, skipna):
+  # metrics.py:816-824   abs(truth - forecast).mean(ensemble_dim)
+  ta, fa, d = align(t, tdims, f, fdims)
+  ax = d.index(ens_dim)
+  return _mean(np.abs(ta - fa), ax, skipna), tuple(
+      x for x in d if x != ens_dim)
+
+
+def crps_spread(f, fdims, ens_dim, lat, lon, region=None, skipna=False):
+  # metrics.py:682-694
+  p, d = pointwise_crps_spread(f, fdims, ens_dim, skipna)
+  return spatial_average(p, d, lat, lon, region, skipna)
+
+
+def crps_skill(f, fdims, t, tdims, ens_dim, lat, lon, region=None,
+               skipna=False):
+  # metrics.py:701-715
+  p, d = pointwise_crps_skill(f, fdims, t, tdims, ens_dim, skipna)
+  return spatial_average(p, d, lat, lon, region, skipna)
+
+
+def crps(f, fdims, t, tdims, ens_dim, lat, lon, region=None, skipna=False):
+  # metrics.py:657-675
+  sk, d1 = crps_skill(f, fdims, t, tdims, ens_dim, lat, lon, region, skipna)
+  sp, d2 = crps_spread(f, fdims, ens_dim, lat, lon, region, skipna)
+  a, b, d = align(sk, d1, sp, d2)
+  return a - 0.5 * b, d
+
+
+def ensemble_mean_mse(f, fdims, t, tdims, ens_dim, lat, lon, region=None,
+                      skipna=False):
+  # metrics.py:1319-1333
+  fdims = tuple(fdims)
+  m = _mean(f, fdims.index(ens_dim), skipna)
+  md = tuple(x for x in fdims if x != ens_dim)
+  ta, ma, d = align(t, tdims, m, md)
+  return spatial_average((ta - ma) ** 2, d, lat, lon, region, skipna)
+
+
+def ensemble_mean_rmse_sqrt_before_time_avg(f, fdims, t, tdims, ens_dim, lat,
+                                            lon, region=None, skipna=False):
+  # metrics.py:1293-1307
+  fdims = tuple(fdims)
+  m = _mean(f, fdims.index(ens_dim), skipna)
+  md = tuple(x for x in fdims if x != ens_dim)
+  ta, ma, d = align(t, tdims, m, md)
+  return spatial_average_l2_norm(ta - ma, d, lat, lon, region, skipna)
+
+
+def ensemble_variance(f, fdims, ens_dim, lat, lon, region=None, skipna=False):
+  # metrics.py:1217-1241
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  od = tuple(x for x in fdims if x != ens_dim)
+  if f.shape[ax] == 1:
+    r, d = spatial_average(f, fdims, lat, lon, region, skipna)
+    r = _mean(r, d.index(ens_dim), skipna)
+    return np.zeros_like(r), tuple(x for x in d if x != ens_dim)
+  return spatial_average(_var(f, ax, skipna), od, lat, lon, region, skipna)
+
+
+def ensemble_stddev_sqrt_before_time_avg(f, fdims, ens_dim, lat, lon,
+                                         region=None, skipna=False):
+  # metrics.py:1185-1210
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  od = tuple(x for x in fdims if x != ens_dim)
+  if f.shape[ax] == 1:
+    r, d = spatial_average(f, fdims, lat, lon, region, skipna)
+    r = _mean(r, d.index(ens_dim), skipna)
+    return np.zeros_like(r), tuple(x for x in d if x != ens_dim)
+  with np.errstate(invalid="ignore"):
+    std = np.sqrt(_var(f, ax, skipna))
+  return spatial_average_l2_norm(std, od, lat, lon, region, skipna)
+
+
+def debiased_ensemble_mean_mse(f, fdims, t, tdims, ens_dim, lat, lon,
+                               region=None, skipna=False):
+  # metrics.py:532-565, 1347-1363
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  n = f.shape[ax]
+  md = tuple(x for x in fdims if x != ens_dim)
+  m = _mean(f, ax, skipna)
+  v = _var(f, ax, skipna)
+  ta, ma, d = align(t, tdims, m, md)
+  biased = (ta - ma) ** 2
+  ba, va, d2 = align(biased, d, v, md)
+  return spatial_average(ba - va / n, d2, lat, lon, region, skipna)
+
+
+def energy_score_skill(f, fdims, t, tdims, ens_dim, lat, lon, region=None,
+                       skipna=False):
+  # metrics.py:1503-1517
+  fa, ta, d = align(f, fdims, t, tdims)
+  r, od = spatial_average_l2_norm(fa - ta, d, lat, lon, region, skipna)
+  return _mean(r, od.index(ens_dim), skipna), tuple(
+      x for x in od if x != ens_dim)
+
+
+def energy_score_spread(f, fdims, ens_dim, lat, lon, region=None,
+                        skipna=False):
+  # metrics.py:1471-1496
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  n = f.shape[ax]
+  if n == 1:
+    r, d = spatial_average(f, fdims, lat, lon, region, skipna)
+    r = _mean(r, d.index(ens_dim), skipna)
+    return np.zeros_like(r), tuple(x for x in d if x != ens_dim)
+  a = np.take(f, np.arange(0, n - 1), axis=ax)
+  b = np.take(f, np.arange(1, n), axis=ax)
+  r, od = spatial_average_l2_norm(a - b, fdims, lat, lon, region, skipna)
+  return _mean(r, od.index(ens_dim), skipna), tuple(
+      x for x in od if x != ens_dim)
+
+
+def energy_score(f, fdims, t, tdims, ens_dim, lat, lon, region=None,
+                 skipna=False):
+  # metrics.py:1446-1464
+  sk, d1 = energy_score_skill(f, fdims, t, tdims, ens_dim, lat, lon, region,
+                              skipna)
+  sp, d2 = energy_score_spread(f, fdims, ens_dim, lat, lon, region, skipna)
+  a, b, d = align(sk, d1, sp, d2)
+  return a - 0.5 * b, d
+
+
+def crps_brute_force(f, fdims, t, tdims, ens_dim, lat, lon, skipna):
+  """The reference's own O(M^2) cross-check, metrics_test.py:896-920."""
+  fdims = tuple(fdims)
+  n = f.shape[fdims.index(ens_dim)]
+  ta, fa, d = align(t, tdims, f, fdims)
+  r, od = spatial_average(np.abs(ta - fa), d, lat, lon, None, skipna)
+  skill = _mean(r, od.index(ens_dim), skipna)
+  odr = tuple(x for x in od if x != ens_dim)
+  if n == 1:
+    spread = np.zeros_like(skill)
+  else:
+    gd = tuple("dummy" if x == ens_dim else x for x in fdims)
+    a, b, d2 = align(f, fdims, f, gd)
+    r2, od2 = spatial_average(np.abs(a - b), d2, lat, lon, None, skipna)
+    r2 = _mean(r2, od2.index(ens_dim), skipna)
+    od2 = tuple(x for x in od2 if x != ens_dim)
+    r2 = _mean(r2, od2.index("dummy"), skipna)
+    od2 = tuple(x for x in od2 if x != "dummy")
+    a, b, odr = align(skill, odr, r2 * (n / (n - 1)), od2)
+    skill, spread = a, b
+  return {"score": skill - 0.5 * spread, "spread": spread, "skill": skill}, odr
+
+
+# ----------------------------------------------------------------------------
+# Conservative regridding -- weatherbench2/regridding.py:297-536
+# The reference runs this in JAX with x64 disabled => float32 everywhere.
+# `dtype` selects the arithmetic type (np.float32 = reference behaviour).
+# ----------------------------------------------------------------------------
+def _rg_latitude_cell_bounds(x, include_poles=True):
+  # regridding.py:302-309
+  if include_poles:
+    initial = np.array([-90], dtype=x.dtype)
+    final = np.array([90], dtype=x.dtype)
+  else:
+    initial = x[:1] - (x[1] - x[0]) / 2
+    final = x[-1:] + (x[-1] - x[-2]) / 2
+  return np.concatenate([initial, (x[:-1] + x[1:]) / 2, final])
+
+
+def _rg_latitude_area_from_bounds(lower, upper):
+  # regridding.py:312-314
+  return np.sin(np.deg2rad(upper)) - np.sin(np.deg2rad(lower))
+
+
+def _rg_latitude_area(points, include_poles):
+  # regridding.py:317-320
+  b = _rg_latitude_cell_bounds(points, include_poles)
+  return _rg_latitude_area_from_bounds(b[:-1], b[1:])
+
+
+def _rg_latitude_overlap(src, tgt, src_poles, tgt_poles):
+  # regridding.py:323-338
+  sb = _rg_latitude_cell_bounds(src, src_poles)
+  tb = _rg_latitude_cell_bounds(tgt, tgt_poles)
+  upper = np.minimum(tb[1:, None], sb[None, 1:])
+  lower = np.maximum(tb[:-1, None], sb[None, :-1])
+  return (upper > lower) * _rg_latitude_area_from_bounds(lower, upper)
+
+
+def conservative_latitude_weights(src, tgt, src_poles, tgt_poles,
+                                  dtype=np.float32):
+  # regridding.py:341-373
+  src = np.asarray(src, dtype=dtype)
+  tgt = np.asarray(tgt, dtype=dtype)
+  _assert_increasing(src)
+  _assert_increasing(tgt)
+  overlap = _rg_latitude_overlap(src, tgt, src_poles, tgt_poles)
+  coverage = np.sum(overlap, axis=1, keepdims=True)
+  with np.errstate(invalid="ignore", divide="ignore"):
+    weights = overlap / coverage
+  if not src_poles:
+    target_areas = _rg_latitude_area(tgt, tgt_poles)[:, None]
+    is_covered = np.isclose(coverage, target_areas, rtol=1e-3)
+    weights = np.where(is_covered, weights, np.nan)
+  return weights.astype(dtype)
+
+
+def align_phase_with(x, target, period):
+  # regridding.py:376-395
+  if period is None:
+    return x
+  shift_down = x > target + period / 2
+  shift_up = x < target - period / 2
+  return x + period * shift_up - period * shift_down
+
+
+def _periodic_upper_bounds(x, period):
+  # regridding.py:398-405
+  if period is None:
+    x_plus = np.concatenate([x[1:], x[-1:] + (x[-1] - x[-2])])
+  else:
+    x_plus = align_phase_with(np.roll(x, -1), x, period)
+  return (x + x_plus) / 2
+
+
+def _periodic_lower_bounds(x, period):
+  # regridding.py:408-415
+  if period is None:
+    x_minus = np.concatenate([x[:1] - (x[1] - x[0]), x[:-1]])
+  else:
+    x_minus = align_phase_with(np.roll(x, +1), x, period)
+  return (x_minus + x) / 2
+
+
+def _periodic_upper_lower_bounds(x, period):
+  # regridding.py:418-423
+  if period is not None:
+    x = x % period
+  return _periodic_upper_bounds(x, period), _periodic_lower_bounds(x, period)
+
+
+def _longitude_length(points, periodic):
+  # regridding.py:426-429
+  upper, lower = _periodic_upper_lower_bounds(points, 360 if periodic else None)
+  return upper - lower
+
+
+def _periodic_overlap(x0, x1, y0, y1, period):
+  # regridding.py:432-438
+  y0 = align_phase_with(y0, x0, period)
+  y1 = align_phase_with(y1, x0, period)
+  upper = np.minimum(x1, y1)
+  lower = np.maximum(x0, y0)
+  return np.maximum(upper - lower, 0)
+
+
+def _longitude_overlap(first, second, first_periodic, second_periodic):
+  # regridding.py:441-459
+  fu, fl = _periodic_upper_lower_bounds(first, 360 if first_periodic else None)
+  su, sl = _periodic_upper_lower_bounds(
+      second, 360 if second_periodic else None)
+  return _periodic_overlap(fl[:, None], fu[:, None], sl[None, :], su[None, :],
+                           360)
+
+
+def conservative_longitude_weights(src, tgt, src_periodic, tgt_periodic,
+                                   dtype=np.float32):
+  # regridding.py:462-499
+  src = np.asarray(src, dtype=dtype)
+  tgt = np.asarray(tgt, dtype=dtype)
+  if len(tgt) < 3 and tgt_periodic:
+    raise ValueError(
+        "Need 3 or more target points else overlap is not well defined. Found"
+        f" {len(tgt)}")
+  _assert_increasing(src)
+  _assert_increasing(tgt)
+  overlap = _longitude_overlap(tgt, src, tgt_periodic, src_periodic)
+  coverage = np.sum(overlap, axis=1, keepdims=True)
+  with np.errstate(invalid="ignore", divide="ignore"):
+    weights = overlap / coverage
+  if not src_periodic:
+    target_lengths = _longitude_length(tgt, tgt_periodic)[:, None]
+    is_covered = np.isclose(coverage, target_lengths, rtol=1e-3)
+    weights = np.where(is_covered, weights, np.nan)
+  return weights.astype(dtype)
+
+
+@dataclasses.dataclass(frozen=True, eq=False)
+class Grid:
+  """regridding.py:117-179."""
+  longitudes: np.ndarray
+  latitudes: np.ndarray
+  periodic: bool = True
+  includes_poles: bool = True
+
+  def __post_init__(self):
+    _assert_increasing(np.asarray(self.latitudes))  # regridding.py:137-138
+
+  @property
+  def shape(self):
+    return (len(self.longitudes), len(self.latitudes))
+
+
+def conservative_regrid(field, source: Grid, target: Grid, dtype=np.float32):
+  """ConservativeRegridder.regrid_array == _nanmean, regridding.py:502-536.
+  `field` has dims (..., lon, lat); arithmetic in `dtype` (reference: f32)."""
+  lon_w = conservative_longitude_weights(
+      source.longitudes, target.longitudes, source.periodic, target.periodic,
+      dtype)
+  lat_w = conservative_latitude_weights(
+      source.latitudes, target.latitudes, source.includes_poles,
+      target.includes_poles, dtype)
+  field = np.asarray(field).astype(dtype)
+  nulls = np.isnan(field)
+
+  def _mean(x):  # regridding.py:505-526
+    with np.errstate(invalid="ignore", over="ignore"):
+      return np.einsum("ab,cd,...bd->...ac", lon_w, lat_w, x.astype(dtype),
+                       optimize=True).astype(dtype)
+
+  total = _mean(np.where(nulls, 0, field))
+  count = _mean(np.logical_not(nulls))
+  with np.errstate(invalid="ignore", divide="ignore"):
+    return (total / count).astype(dtype)  # NaN if count == 0 (:534)
+
+
+# ----------------------------------------------------------------------------
+# Zonal energy spectrum -- weatherbench2/derived_variables.py:531-626
+# ----------------------------------------------------------------------------
+def circumference(lat):
+  # derived_variables.py:578-581
+  return np.cos(np.asarray(lat) * np.pi / 180) * (2 * np.pi * EARTH_RADIUS_M)
+
+
+def lon_spacing_m(lat, lon):
+  # derived_variables.py:583-590
+  diffs = np.diff(np.asarray(lon))
+  if np.max(np.abs(diffs - diffs[0])) > 1e-3:
+    raise ValueError(f"Expected uniform longitude spacing. {lon=}")
+  return circumference(lat) * diffs[0] / 360
+
+
+def zonal_energy_spectrum(x, dims, lat, lon):
+  """derived_variables.py:592-626.  Returns (spectrum, dims, frequency,
+  wavelength); `longitude` is replaced by `zonal_wavenumber` as the LAST dim
+  (apply_ufunc moves the core dim to the end)."""
+  dims = tuple(dims)
+  x = np.asarray(x)
+  spacing = lon_spacing_m(lat, lon)
+  ax = dims.index(LON)
+  xm = np.moveaxis(x, ax, -1)
+  out_dims = tuple(d for d in dims if d != LON) + ("zonal_wavenumber",)
+  f_k = np.fft.rfft(xm, axis=-1, norm="forward")  # :597
+  one_and_many_twos = np.concatenate(([1], [2] * (f_k.shape[-1] - 1)))  # :600
+  spectrum = np.real(f_k * np.conj(f_k)) * one_and_many_twos
+  base_frequency = np.fft.rfftfreq(len(lon))  # :614
+  with np.errstate(divide="ignore"):
+    frequency = base_frequency[:, None] / spacing[None, :]  # (k, lat)  :618
+    wavelength = 1 / frequency  # :621
+  # multiply by circumference, broadcast along latitude  (:626)
+  ilat = out_dims.index(LAT)
+  shape = [1] * spectrum.ndim
+  shape[ilat] = len(lat)
+  spectrum = spectrum * circumference(lat).reshape(shape)
+  return spectrum, out_dims, frequency, wavelength
