@@ -1,0 +1,220 @@
+/* wb2b200.h -- C ABI of the B200-native WeatherBench2 hot path (libwb2b200.so).
+ *
+ * The reference (google-research/weatherbench2) is pure Python and has no FFI of
+ * its own; these entry points are what its operator classes bind through
+ * ctypes.  Each entry point cites the reference interface
+ * it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative WB2_E* code on failure and
+ *     never throws/aborts; wb2_last_error() gives the message (thread-local);
+ *   - the caller owns every data buffer.  "dev" pointers are CUDA device
+ *     pointers on the context's device, "host" pointers are ordinary host
+ *     memory (pinned or pageable);  small descriptor arrays (weights, offset
+ *     tables) are ALWAYS host pointers and are copied by the library;
+ *   - kernels are enqueued on the context's stream; results written to device
+ *     memory are ordered on that stream (wb2_synchronize / wb2_memcpy_d2h to
+ *     read them);  the *_host entry points are synchronous end to end;
+ *   - outputs are raw weighted SUMS (and weight sums) in float64; division,
+ *     sqrt, ACC ratio, CRPS = skill - spread/2 stay in the Python operator so
+ *     the NaN / zero-weight rules remain visible (weatherbench2/metrics.py:161);
+ *   - reductions are deterministic (fixed-order tree, no float atomics).
+ *
+ * Field addressing.  A "field" is one 2-D (row, col) slab with `col`
+ * contiguous: (latitude, longitude) for raw 0.25-degree data or
+ * (longitude, latitude) for the reference's mock / regridded layout
+ * (weatherbench2/schema.py:83).  Operands are addressed by a base pointer plus
+ * a per-field element-offset table, so broadcasting (truth without lead_time),
+ * the by-init gather `truth.sel(time=valid_time)` (evaluation.py:475) and the
+ * climatology day-of-year lookup (metrics.py:398-404) need no materialised
+ * copies.
+ */
+#ifndef WB2B200_H_
+#define WB2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB2_VERSION 100 /* 0.1.0 */
+
+enum {
+  WB2_OK = 0,
+  WB2_EINVAL = -1,   /* bad argument */
+  WB2_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+  WB2_ENOMEM = -3,
+  WB2_EUNSUPPORTED = -4
+};
+
+enum { WB2_F32 = 0, WB2_F64 = 1 };
+
+#define WB2_MAX_REGIONS 32
+
+/* number of per-(field, region) float64 outputs of wb2_det_metrics */
+#define WB2_DET_NSTAT 10
+/* [0] sum W*d^2   [1] sum W*|d|   [2] sum W*d          (d  = f - t)
+ * [3] sum W*fa*ta [4] sum W*fa^2  [5] sum W*ta^2       (fa = f - c, ta = t - c)
+ * [6] sum W*[d valid] [7] sum W*[fa*ta valid] [8] sum W*[fa valid]
+ * [9] sum W*[ta valid]   -- the xarray `sum_of_weights` of each average     */
+
+/* number of per-(field, region) float64 outputs of wb2_ens_metrics */
+#define WB2_ENS_NSTAT 10
+/* [0] sum W*skill_pt      skill_pt  = mean_m |t - x_m|        (metrics.py:824)
+ * [1] sum W*spread_pt     spread_pt = 2 mean_m((2r_m-M-1)x_m)/(M-1)  (:805-813)
+ * [2] sum W*(t - xbar)^2                                       (metrics.py:1330)
+ * [3] sum W*var_ddof1                                          (metrics.py:1238)
+ * [4] sum W*((t - xbar)^2 - var/M)                             (metrics.py:564-565)
+ * [5..9] the matching sums of W*[value valid]                                */
+
+typedef struct wb2_ctx wb2_ctx;
+
+/* Region / latitude weights of one launch.  The weight of cell (row, col) for
+ * region r is   W_r = row_w[r][row] * seg_w[r][seg(col)] * col_w[col] * cell_w[row][col]
+ * where seg(col) = k for seg_start[k] <= col < seg_start[k+1].
+ * This factorisation holds every reference region exactly
+ * (weatherbench2/regions.py:57-158): latitude weights and latitude boxes go in
+ * row_w (or col_w*seg_w for the latitude-fastest layout), longitude boxes in
+ * seg_w (or row_w), a LandRegion mask in cell_w.
+ * zero_skip != 0 reproduces `dataset.where(weights > 0, 0)` (metrics.py:160):
+ * cells whose weight is zero contribute nothing, even when they hold NaN/Inf. */
+typedef struct {
+  int32_t nrow;            /* slow spatial axis length                         */
+  int32_t ncol;            /* contiguous spatial axis length                   */
+  int64_t row_stride;      /* elements between consecutive rows (>= ncol)      */
+  int32_t nregion;         /* 1..WB2_MAX_REGIONS                               */
+  int32_t nseg;            /* >= 1                                             */
+  const double* row_w;     /* host [nregion][nrow]                             */
+  const int32_t* seg_start;/* host [nseg + 1], seg_start[0]=0, [nseg]=ncol     */
+  const double* seg_w;     /* host [nregion][nseg]                             */
+  const float* col_w;      /* host [ncol] or NULL (== all ones)                */
+  const float* cell_w;     /* DEVICE [nrow][ncol] (dense) or NULL              */
+  int32_t zero_skip;
+} wb2_weights;
+
+/* ---- library / context ---------------------------------------------------- */
+int wb2_version(void);
+const char* wb2_last_error(void);
+/* 1 when the library was built with the CUDA kernels (always, for this .so)   */
+int wb2_has_cuda(void);
+/* number of kernels this context has launched since creation (bench evidence) */
+int64_t wb2_launch_count(const wb2_ctx* ctx);
+
+int wb2_create(int device, wb2_ctx** out);
+int wb2_destroy(wb2_ctx* ctx);
+/* use an external cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int wb2_set_stream(wb2_ctx* ctx, void* cuda_stream);
+void* wb2_get_stream(wb2_ctx* ctx);
+int wb2_synchronize(wb2_ctx* ctx);
+
+int wb2_malloc(wb2_ctx* ctx, size_t bytes, void** dev_ptr);
+int wb2_free(wb2_ctx* ctx, void* dev_ptr);
+int wb2_host_alloc(wb2_ctx* ctx, size_t bytes, void** host_ptr); /* pinned */
+int wb2_host_free(wb2_ctx* ctx, void* host_ptr);
+int wb2_memcpy_h2d(wb2_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int wb2_memcpy_d2h(wb2_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+int wb2_memset(wb2_ctx* ctx, void* dev_ptr, int value, size_t bytes);
+
+/* ---- K1: deterministic metrics ---------------------------------------------
+ * Replaces the arithmetic of  MSE / RMSESqrtBeforeTimeAvg / MAE / Bias / ACC
+ * .compute_chunk (weatherbench2/metrics.py:251-269, 283-301, 323-330, 352-359,
+ * 387-414) and of _spatial_average (metrics.py:141-163) for ALL regions of an
+ * eval config in one pass over the data (evaluation.py:408-435 loops
+ * metric x region and re-reads the chunk every time).
+ *   f, t, c      device base pointers (c may be NULL: no climatology -> stats
+ *                3,4,5,7,8,9 are written as 0)
+ *   dtype        WB2_F32 / WB2_F64 element type of f, t and c
+ *   off_f/t/c    host [nfield] element offsets of each field's slab
+ *   skipna       0: NaN propagates into the sums (stats 6..9 then hold the
+ *                plain weight sums);  1: NaN cells are skipped per statistic
+ *   out          device [nfield][nregion][WB2_DET_NSTAT] float64
+ */
+int wb2_det_metrics(wb2_ctx* ctx, const void* f, const void* t, const void* c,
+                    int dtype, int64_t nfield, const int64_t* off_f,
+                    const int64_t* off_t, const int64_t* off_c,
+                    const wb2_weights* w, int skipna, double* out);
+
+/* Wind-vector variant: stat[0] = sum W*(du^2 + dv^2), stat[6] its weight sum
+ * (WindVectorMSE.compute_chunk, metrics.py:189-202); other stats are 0.       */
+int wb2_det_metrics_vector(wb2_ctx* ctx, const void* fu, const void* fv,
+                           const void* tu, const void* tv, int dtype,
+                           int64_t nfield, const int64_t* off_fu,
+                           const int64_t* off_fv, const int64_t* off_tu,
+                           const int64_t* off_tv, const wb2_weights* w,
+                           int skipna, double* out);
+
+/* Same as wb2_det_metrics but f, t, c are HOST base pointers and `out` is a
+ * host array: the library streams the slabs through double-buffered device
+ * staging (H2D on a copy stream overlapped with the kernel) and returns after
+ * the result is in `out`.  This is the end-to-end entry the Python operators
+ * use for NumPy inputs.  cell_w in `w` must still be a device pointer.        */
+int wb2_det_metrics_host(wb2_ctx* ctx, const void* f, const void* t,
+                         const void* c, int dtype, int64_t nfield,
+                         const int64_t* off_f, const int64_t* off_t,
+                         const int64_t* off_c, const wb2_weights* w, int skipna,
+                         double* out_host);
+
+/* ---- K2: ensemble metrics --------------------------------------------------
+ * Replaces CRPS / CRPSSkill / CRPSSpread, EnsembleMeanMSE / RMSE,
+ * EnsembleVariance / Stddev, DebiasedEnsembleMeanMSE .compute_chunk
+ * (metrics.py:657-715, 1185-1241, 1293-1363) incl. _rankdata (:836-846):
+ * all five point-wise quantities from ONE read of the M members.
+ *   x            device base pointer of the ensemble forecast
+ *   off_x        host [nfield] offset of member 0 of each field
+ *   member_stride elements between consecutive members of the same cell
+ *   t, off_t     truth slab per field
+ *   out          device [nfield][nregion][WB2_ENS_NSTAT] float64
+ */
+int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                    int32_t nmember, int64_t member_stride, int64_t nfield,
+                    const int64_t* off_x, const int64_t* off_t,
+                    const wb2_weights* w, int skipna, double* out);
+
+/* ---- K5: conservative regridding -------------------------------------------
+ * Replaces ConservativeRegridder.regrid_array (= _nanmean,
+ * weatherbench2/regridding.py:502-536).  The two weight matrices
+ * (regridding.py:341-373, 462-499) are banded; they are passed in CSR form
+ * built by the Python operator with the reference's own formulas.
+ * Input slabs are (lon_src, lat_src) with lat contiguous, output slabs
+ * (lon_tgt, lat_tgt) float32, exactly the reference's layout (regridding.py:190).
+ * A NaN weight row (target cell not covered, regridding.py:367-371) is flagged
+ * by a negative tap count and yields NaN.
+ */
+typedef struct {
+  int32_t n_src;            /* source axis length                              */
+  int32_t n_tgt;            /* target axis length                              */
+  const int32_t* row_ptr;   /* host [n_tgt + 1] CSR offsets; row_ptr[i+1] <
+                               row_ptr[i] never happens; uncovered rows have
+                               zero taps and nan_row[i] = 1                    */
+  const int32_t* col_idx;   /* host [nnz] source indices                       */
+  const float* val;         /* host [nnz] weights (rows sum to 1)              */
+  const uint8_t* nan_row;   /* host [n_tgt] 1 = output NaN                     */
+} wb2_csr;
+
+int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* dst,
+                            int64_t nfield, int64_t src_field_stride,
+                            int64_t dst_field_stride, const wb2_csr* lon_w,
+                            const wb2_csr* lat_w);
+
+/* ---- K4: zonal energy spectrum ---------------------------------------------
+ * Replaces ZonalEnergySpectrum.compute (weatherbench2/derived_variables.py:
+ * 592-626): rfft(norm='forward') along longitude, |F_k|^2 * (1 if k==0 else 2),
+ * times `scale[row]` (the latitude circumference, derived_variables.py:626).
+ *   x      device [nfield][nrow][ncol] float32, ncol = number of longitudes
+ *   scale  host [nrow] float64
+ *   out    device float32; accumulate == 0: [nfield][nrow][ncol/2+1] written;
+ *          accumulate == 1: out has [nfield_out][nrow][ncol/2+1] and field i
+ *          is ADDED to slot  i % nfield_out  (device-side time-sum for the
+ *          script's `xbeam.Mean(['time'])`,
+ *          scripts/compute_zonal_energy_spectrum.py:234)
+ */
+int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield,
+                       int32_t nrow, int32_t ncol, const double* scale,
+                       float* out, int32_t accumulate, int64_t nfield_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WB2B200_H_ */

@@ -1,0 +1,339 @@
+"""ctypes binding of libwb2b200.so (the C ABI in include/wb2b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no B200 is
+visible when a context is created, the calls raise `Wb2Error`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libwb2b200.so')
+
+F32, F64 = 0, 1
+MAX_REGIONS = 32
+DET_NSTAT = 10
+ENS_NSTAT = 10
+
+
+class Wb2Error(RuntimeError):
+  """Raised when the native library reports an error (or is missing)."""
+
+
+class Weights(C.Structure):
+  """struct wb2_weights (include/wb2b200.h)."""
+  _fields_ = [
+      ('nrow', C.c_int32),
+      ('ncol', C.c_int32),
+      ('row_stride', C.c_int64),
+      ('nregion', C.c_int32),
+      ('nseg', C.c_int32),
+      ('row_w', C.POINTER(C.c_double)),
+      ('seg_start', C.POINTER(C.c_int32)),
+      ('seg_w', C.POINTER(C.c_double)),
+      ('col_w', C.POINTER(C.c_float)),
+      ('cell_w', C.c_void_p),
+      ('zero_skip', C.c_int32),
+  ]
+
+
+class Csr(C.Structure):
+  """struct wb2_csr (include/wb2b200.h)."""
+  _fields_ = [
+      ('n_src', C.c_int32),
+      ('n_tgt', C.c_int32),
+      ('row_ptr', C.POINTER(C.c_int32)),
+      ('col_idx', C.POINTER(C.c_int32)),
+      ('val', C.POINTER(C.c_float)),
+      ('nan_row', C.POINTER(C.c_uint8)),
+  ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_P = C.c_void_p
+_I64P = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/wb2b200.h declares
+PROTOTYPES = {
+    'wb2_version': (C.c_int, []),
+    'wb2_last_error': (C.c_char_p, []),
+    'wb2_has_cuda': (C.c_int, []),
+    'wb2_launch_count': (C.c_int64, [_P]),
+    'wb2_create': (C.c_int, [C.c_int, C.POINTER(_P)]),
+    'wb2_destroy': (C.c_int, [_P]),
+    'wb2_set_stream': (C.c_int, [_P, _P]),
+    'wb2_get_stream': (_P, [_P]),
+    'wb2_synchronize': (C.c_int, [_P]),
+    'wb2_malloc': (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    'wb2_free': (C.c_int, [_P, _P]),
+    'wb2_host_alloc': (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    'wb2_host_free': (C.c_int, [_P, _P]),
+    'wb2_memcpy_h2d': (C.c_int, [_P, _P, _P, C.c_size_t]),
+    'wb2_memcpy_d2h': (C.c_int, [_P, _P, _P, C.c_size_t]),
+    'wb2_memset': (C.c_int, [_P, _P, C.c_int, C.c_size_t]),
+    'wb2_det_metrics': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, _I64P,
+                                  _I64P, _I64P, C.POINTER(Weights), C.c_int,
+                                  _P]),
+    'wb2_det_metrics_vector': (C.c_int, [_P, _P, _P, _P, _P, C.c_int,
+                                         C.c_int64, _I64P, _I64P, _I64P, _I64P,
+                                         C.POINTER(Weights), C.c_int, _P]),
+    'wb2_det_metrics_host': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64,
+                                       _I64P, _I64P, _I64P, C.POINTER(Weights),
+                                       C.c_int, _P]),
+    'wb2_ens_metrics': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
+                                  C.c_int64, _I64P, _I64P, C.POINTER(Weights),
+                                  C.c_int, _P]),
+    'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
+                                          C.c_int64, C.POINTER(Csr),
+                                          C.POINTER(Csr)]),
+    'wb2_zonal_spectrum': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_double), _P, C.c_int32,
+                                     C.c_int64]),
+}
+
+
+def load_library():
+  """Loads libwb2b200.so (once).  Raises Wb2Error if it has not been built."""
+  global _lib
+  with _lib_lock:
+    if _lib is not None:
+      return _lib
+    if not os.path.exists(LIB_PATH):
+      raise Wb2Error(
+          f'{LIB_PATH} not found: build it with '
+          '`python -c "import __graft_entry__ as g; g.build()"` or '
+          '`make -C weatherbench2_b200/csrc`.  There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+      fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+      fn.restype = restype
+      fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+  if rc != 0:
+    msg = load_library().wb2_last_error()
+    raise Wb2Error(f'libwb2b200 error {rc}: {msg.decode() if msg else "?"}')
+
+
+def _as_ptr(a: Optional[np.ndarray], ctype):
+  if a is None:
+    return None
+  return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+  """A wb2_ctx: one CUDA device + stream + descriptor arenas."""
+
+  def __init__(self, device: int = 0):
+    self.lib = load_library()
+    h = _P()
+    check(self.lib.wb2_create(int(device), C.byref(h)))
+    self.handle = h
+    self.device = int(device)
+    self._closed = False
+
+  def close(self):
+    if not self._closed:
+      self._closed = True
+      self.lib.wb2_destroy(self.handle)
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  # -- streams / memory -------------------------------------------------------
+  def set_stream(self, cuda_stream: int):
+    check(self.lib.wb2_set_stream(self.handle, _P(cuda_stream)))
+
+  def synchronize(self):
+    check(self.lib.wb2_synchronize(self.handle))
+
+  @property
+  def launch_count(self) -> int:
+    return int(self.lib.wb2_launch_count(self.handle))
+
+  def malloc(self, nbytes: int) -> int:
+    p = _P()
+    check(self.lib.wb2_malloc(self.handle, nbytes, C.byref(p)))
+    return p.value
+
+  def free(self, ptr: int):
+    check(self.lib.wb2_free(self.handle, _P(ptr)))
+
+  def host_alloc(self, nbytes: int) -> int:
+    p = _P()
+    check(self.lib.wb2_host_alloc(self.handle, nbytes, C.byref(p)))
+    return p.value
+
+  def host_free(self, ptr: int):
+    check(self.lib.wb2_host_free(self.handle, _P(ptr)))
+
+  def pinned_empty(self, shape, dtype) -> np.ndarray:
+    """NumPy array backed by pinned host memory (freed with the context)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = self.host_alloc(max(n, 1))
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape)))
+    return arr.reshape(shape)
+
+  def to_device(self, a: np.ndarray) -> int:
+    a = np.ascontiguousarray(a)
+    p = self.malloc(a.nbytes)
+    check(self.lib.wb2_memcpy_h2d(self.handle, _P(p), _P(a.ctypes.data),
+                                  a.nbytes))
+    return p
+
+  def from_device(self, ptr: int, shape, dtype) -> np.ndarray:
+    out = np.empty(shape, dtype=dtype)
+    check(self.lib.wb2_memcpy_d2h(self.handle, _P(out.ctypes.data), _P(ptr),
+                                  out.nbytes))
+    return out
+
+  # -- K1 ---------------------------------------------------------------------
+  def det_metrics(self, f: int, t: int, c: Optional[int], dtype: int,
+                  off_f: np.ndarray, off_t: np.ndarray,
+                  off_c: Optional[np.ndarray], weights: 'WeightSpec',
+                  skipna: bool, out: int, host: bool = False):
+    """f/t/c/out are raw addresses (device, or host when host=True)."""
+    nfield = int(off_f.size)
+    w = weights.as_struct()
+    fn = self.lib.wb2_det_metrics_host if host else self.lib.wb2_det_metrics
+    check(fn(self.handle, _P(f), _P(t), _P(c) if c else None, dtype, nfield,
+             _as_ptr(off_f, C.c_int64), _as_ptr(off_t, C.c_int64),
+             _as_ptr(off_c, C.c_int64) if off_c is not None else None,
+             C.byref(w), int(bool(skipna)), _P(out)))
+
+  def det_metrics_vector(self, fu, fv, tu, tv, dtype, off_fu, off_fv, off_tu,
+                         off_tv, weights: 'WeightSpec', skipna: bool, out: int):
+    w = weights.as_struct()
+    check(self.lib.wb2_det_metrics_vector(
+        self.handle, _P(fu), _P(fv), _P(tu), _P(tv), dtype, int(off_fu.size),
+        _as_ptr(off_fu, C.c_int64), _as_ptr(off_fv, C.c_int64),
+        _as_ptr(off_tu, C.c_int64), _as_ptr(off_tv, C.c_int64), C.byref(w),
+        int(bool(skipna)), _P(out)))
+
+  # -- K2 ---------------------------------------------------------------------
+  def ens_metrics(self, x: int, t: int, dtype: int, nmember: int,
+                  member_stride: int, off_x: np.ndarray, off_t: np.ndarray,
+                  weights: 'WeightSpec', skipna: bool, out: int):
+    w = weights.as_struct()
+    check(self.lib.wb2_ens_metrics(
+        self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
+        int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
+        C.byref(w), int(bool(skipna)), _P(out)))
+
+  # -- K5 ---------------------------------------------------------------------
+  def regrid_conservative(self, src: int, dst: int, nfield: int,
+                          src_stride: int, dst_stride: int, lon_w: 'CsrSpec',
+                          lat_w: 'CsrSpec'):
+    a, b = lon_w.as_struct(), lat_w.as_struct()
+    check(self.lib.wb2_regrid_conservative(
+        self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
+        int(dst_stride), C.byref(a), C.byref(b)))
+
+  # -- K4 ---------------------------------------------------------------------
+  def zonal_spectrum(self, x: int, nfield: int, nrow: int, ncol: int,
+                     scale: np.ndarray, out: int, accumulate: bool = False,
+                     nfield_out: int = 0):
+    scale = np.ascontiguousarray(scale, dtype=np.float64)
+    check(self.lib.wb2_zonal_spectrum(
+        self.handle, _P(x), int(nfield), int(nrow), int(ncol),
+        _as_ptr(scale, C.c_double), _P(out), int(bool(accumulate)),
+        int(nfield_out)))
+
+
+class WeightSpec:
+  """Host-side owner of the arrays a wb2_weights struct points to."""
+
+  def __init__(self, nrow, ncol, row_w, seg_start, seg_w, col_w=None,
+               cell_w_dev: Optional[int] = None, zero_skip=False,
+               row_stride=None):
+    self.nrow, self.ncol = int(nrow), int(ncol)
+    self.row_stride = int(row_stride if row_stride is not None else ncol)
+    self.row_w = np.ascontiguousarray(row_w, dtype=np.float64).reshape(
+        -1, self.nrow)
+    self.nregion = self.row_w.shape[0]
+    self.seg_start = np.ascontiguousarray(seg_start, dtype=np.int32)
+    self.nseg = self.seg_start.size - 1
+    self.seg_w = np.ascontiguousarray(seg_w, dtype=np.float64).reshape(
+        self.nregion, self.nseg)
+    self.col_w = (None if col_w is None else
+                  np.ascontiguousarray(col_w, dtype=np.float32))
+    self.cell_w_dev = cell_w_dev
+    self.zero_skip = bool(zero_skip)
+
+  def as_struct(self) -> Weights:
+    w = Weights()
+    w.nrow, w.ncol, w.row_stride = self.nrow, self.ncol, self.row_stride
+    w.nregion, w.nseg = self.nregion, self.nseg
+    w.row_w = _as_ptr(self.row_w, C.c_double)
+    w.seg_start = _as_ptr(self.seg_start, C.c_int32)
+    w.seg_w = _as_ptr(self.seg_w, C.c_double)
+    w.col_w = _as_ptr(self.col_w, C.c_float) if self.col_w is not None else None
+    w.cell_w = self.cell_w_dev
+    w.zero_skip = int(self.zero_skip)
+    return w
+
+
+class CsrSpec:
+  """Host-side owner of a wb2_csr (banded regridding weights)."""
+
+  def __init__(self, dense: np.ndarray):
+    dense = np.asarray(dense, dtype=np.float32)
+    self.n_tgt, self.n_src = dense.shape
+    nan_row = np.isnan(dense).any(axis=1)
+    row_ptr = [0]
+    cols, vals = [], []
+    for i in range(self.n_tgt):
+      if not nan_row[i]:
+        nz = np.nonzero(dense[i])[0]
+        cols.append(nz)
+        vals.append(dense[i, nz])
+      row_ptr.append(row_ptr[-1] + (0 if nan_row[i] else nz.size))
+    self.row_ptr = np.asarray(row_ptr, dtype=np.int32)
+    self.col_idx = (np.concatenate(cols).astype(np.int32) if cols
+                    else np.zeros(0, np.int32))
+    self.val = (np.concatenate(vals).astype(np.float32) if vals
+                else np.zeros(0, np.float32))
+    if self.col_idx.size == 0:  # keep pointers valid
+      self.col_idx = np.zeros(1, np.int32)
+      self.val = np.zeros(1, np.float32)
+    self.nan_row = nan_row.astype(np.uint8)
+
+  def as_struct(self) -> Csr:
+    s = Csr()
+    s.n_src, s.n_tgt = self.n_src, self.n_tgt
+    s.row_ptr = _as_ptr(self.row_ptr, C.c_int32)
+    s.col_idx = _as_ptr(self.col_idx, C.c_int32)
+    s.val = _as_ptr(self.val, C.c_float)
+    s.nan_row = _as_ptr(self.nan_row, C.c_uint8)
+    return s
+
+
+_default_ctx = {}
+_ctx_lock = threading.Lock()
+
+
+def default_context(device: Optional[int] = None) -> Context:
+  """Process-wide context per device (device defaults to LOCAL_RANK or 0)."""
+  if device is None:
+    device = int(os.environ.get('WB2_DEVICE', os.environ.get('LOCAL_RANK', 0)))
+  with _ctx_lock:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+      ctx = Context(device)
+      _default_ctx[device] = ctx
+    return ctx

@@ -1,0 +1,381 @@
+"""Host-side planning for the spatial-reduction kernels.
+
+Turns named-dimension arrays (NumPy on the host or torch tensors on a CUDA
+device) plus a list of regions into what the C ABI wants: a base pointer and a
+per-field element-offset table for every operand, and a `wb2_weights`
+description of latitude weights x region masks.  Nothing numerical happens
+here except building the (tiny) weight vectors with the reference's own
+formulas (weatherbench2/metrics.py:35-60).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional, Sequence
+
+import numpy as np
+
+from weatherbench2_b200 import _lib
+from weatherbench2_b200 import xarray_lite as xl
+
+LAT, LON = 'latitude', 'longitude'
+
+
+# ---- latitude weights (metrics.py:35-60) -------------------------------------
+def _assert_increasing(x: np.ndarray):
+  if not (np.diff(x) > 0).all():
+    raise ValueError(f'array is not increasing: {x}')
+
+
+def _latitude_cell_bounds(x: np.ndarray) -> np.ndarray:
+  pi_over_2 = np.array([np.pi / 2], dtype=x.dtype)
+  return np.concatenate([-pi_over_2, (x[:-1] + x[1:]) / 2, pi_over_2])
+
+
+def _cell_area_from_latitude(points: np.ndarray) -> np.ndarray:
+  bounds = _latitude_cell_bounds(points)
+  _assert_increasing(bounds)
+  return np.sin(bounds[1:]) - np.sin(bounds[:-1])
+
+
+def lat_weights(latitude_deg: np.ndarray) -> np.ndarray:
+  """Area weights normalised to mean 1 (weatherbench2/metrics.py:55-60)."""
+  w = _cell_area_from_latitude(np.deg2rad(np.asarray(latitude_deg)))
+  return w / np.mean(w)
+
+
+# ---- operand description -----------------------------------------------------
+@dataclasses.dataclass
+class Operand:
+  """One named array prepared for the kernels."""
+  data: object               # np.ndarray or torch.Tensor (kept alive)
+  addr: int                  # address of element 0
+  itemsize: int
+  on_device: bool
+  outer_dims: tuple          # non-spatial dims
+  outer_shape: tuple
+  outer_strides: tuple       # in elements
+  layout: str                # 'lat_lon' (lon contiguous) | 'lon_lat'
+  nrow: int
+  ncol: int
+  row_stride: int
+  dtype: np.dtype
+
+
+def _strides_elems(data) -> tuple:
+  if xl._is_torch(data):  # pylint: disable=protected-access
+    return tuple(int(s) for s in data.stride())
+  return tuple(int(s // data.itemsize) for s in data.strides)
+
+
+def _address(data) -> int:
+  if xl._is_torch(data):  # pylint: disable=protected-access
+    return int(data.data_ptr())
+  return int(data.ctypes.data)
+
+
+def _np_dtype(data) -> np.dtype:
+  if xl._is_torch(data):  # pylint: disable=protected-access
+    return np.dtype(str(data.dtype).replace('torch.', ''))
+  return data.dtype
+
+
+def prepare_operand(da: xl.DataArray, want_layout: Optional[str] = None,
+                    want_dtype: Optional[np.dtype] = None) -> Operand:
+  """Describes `da` for the kernels, copying only when its memory layout is
+  not (…outer…, row, col) with `col` contiguous, or its dtype is neither
+  float32 nor float64."""
+  if LAT not in da.dims or LON not in da.dims:
+    raise ValueError(f'{da.name!r} needs latitude and longitude dims, has '
+                     f'{da.dims}')
+  lazy = getattr(da, 'lazy_source', None)
+  if lazy is not None:
+    # a label gather (e.g. truth.sel(time=valid_time)): address the source
+    # through the offset table instead of materialising the copy
+    source, maps = lazy
+    return gather_operand(prepare_operand(source, want_layout, want_dtype),
+                          maps)
+  data = da.data
+  dims = da.dims
+  torch_in = xl._is_torch(data)  # pylint: disable=protected-access
+  dt = _np_dtype(data)
+  target_dt = np.dtype(want_dtype) if want_dtype is not None else (
+      dt if dt in (np.dtype('float32'), np.dtype('float64'))
+      else np.dtype('float32') if dt.itemsize <= 4 and dt.kind == 'f'
+      else np.dtype('float64'))
+  if dt != target_dt:
+    if torch_in:
+      import torch  # pylint: disable=import-outside-toplevel
+      data = data.to(getattr(torch, target_dt.name))
+    else:
+      data = data.astype(target_dt)
+  strides = _strides_elems(data)
+  ilat, ilon = dims.index(LAT), dims.index(LON)
+  shape = tuple(data.shape)
+
+  def layout_ok():
+    if strides[ilon] == 1 or shape[ilon] == 1:
+      lay = 'lat_lon'
+      if strides[ilat] >= shape[ilon] or shape[ilat] == 1:
+        return lay
+    if strides[ilat] == 1 or shape[ilat] == 1:
+      lay = 'lon_lat'
+      if strides[ilon] >= shape[ilat] or shape[ilon] == 1:
+        return lay
+    return None
+
+  lay = layout_ok()
+  if any(s < 0 for s in strides):
+    lay = None
+  if lay is None or (want_layout is not None and lay != want_layout and not (
+      shape[ilat] == 1 or shape[ilon] == 1)):
+    # contiguous copy with the spatial dims last, in the wanted order
+    order = want_layout or 'lat_lon'
+    sp = (LAT, LON) if order == 'lat_lon' else (LON, LAT)
+    perm_dims = tuple(d for d in dims if d not in sp) + sp
+    perm = [dims.index(d) for d in perm_dims]
+    if torch_in:
+      data = data.permute(*perm).contiguous()
+    else:
+      data = np.ascontiguousarray(np.transpose(data, perm))
+    dims = perm_dims
+    strides = _strides_elems(data)
+    shape = tuple(data.shape)
+    ilat, ilon = dims.index(LAT), dims.index(LON)
+    lay = order
+  if want_layout is not None and lay != want_layout:
+    lay = want_layout  # degenerate size-1 axis: either description is valid
+  if lay == 'lat_lon':
+    nrow, ncol, row_stride = shape[ilat], shape[ilon], strides[ilat]
+  else:
+    nrow, ncol, row_stride = shape[ilon], shape[ilat], strides[ilon]
+  if nrow == 1:
+    row_stride = max(row_stride, ncol)
+  outer = [i for i in range(len(dims)) if i not in (ilat, ilon)]
+  on_dev = bool(torch_in and data.is_cuda)
+  if torch_in and not on_dev:
+    data = data.numpy()
+  return Operand(
+      data=data, addr=_address(data), itemsize=target_dt.itemsize,
+      on_device=on_dev, outer_dims=tuple(dims[i] for i in outer),
+      outer_shape=tuple(shape[i] for i in outer),
+      outer_strides=tuple(strides[i] for i in outer), layout=lay, nrow=nrow,
+      ncol=ncol, row_stride=int(row_stride), dtype=target_dt)
+
+
+def broadcast_dims(*operands: Operand) -> tuple[tuple, tuple]:
+  """Result dims/shape of xarray arithmetic between the operands: dims of the
+  first, then unseen dims of the next ones."""
+  dims, shape = [], []
+  for op in operands:
+    for d, n in zip(op.outer_dims, op.outer_shape):
+      if d in dims:
+        if shape[dims.index(d)] != n:
+          raise ValueError(
+              f'size mismatch along {d!r}: {shape[dims.index(d)]} vs {n}')
+      else:
+        dims.append(d)
+        shape.append(n)
+  return tuple(dims), tuple(shape)
+
+
+def offset_table(op: Operand, dims: tuple, shape: tuple) -> np.ndarray:
+  """Element offset of the slab of `op` for every index of the broadcast outer
+  grid (C order).  Missing dims get stride 0 (broadcast)."""
+  off = np.zeros(shape, dtype=np.int64)
+  gathered = getattr(op, 'gather_terms', None)
+  if gathered is not None:
+    # explicit (dims, offsets) terms: a label lookup folded into the table
+    for tdims, arr in gathered:
+      perm = [tdims.index(d) for d in dims if d in tdims]
+      a = np.transpose(np.asarray(arr, dtype=np.int64), perm)
+      a = a[tuple(slice(None) if d in tdims else None for d in dims)]
+      off = off + a
+    return np.ascontiguousarray(np.broadcast_to(off, shape)).reshape(-1)
+  for ax, (d, n) in enumerate(zip(dims, shape)):
+    if d in op.outer_dims:
+      st = op.outer_strides[op.outer_dims.index(d)]
+      sh = [1] * len(shape)
+      sh[ax] = n
+      off = off + (np.arange(n, dtype=np.int64) * st).reshape(sh)
+  return np.ascontiguousarray(off).reshape(-1)
+
+
+def gather_operand(op: Operand, index_maps: dict) -> Operand:
+  """Re-addresses `op` through label lookups without copying data.
+
+  index_maps: {source_dim: (new_dims, positions)} -- `source_dim` of `op` is
+  indexed by the integer array `positions` whose dims are `new_dims`
+  (xarray's vectorised `.sel`, e.g. the day-of-year / hour lookup of
+  weatherbench2/metrics.py:398-404 or `truth.sel(time=valid_time)`,
+  evaluation.py:475).  Untouched outer dims keep their stride addressing.
+  """
+  terms = []
+  new_dims, new_shape = [], []
+
+  def add_dim(d, n):
+    if d in new_dims:
+      if new_shape[new_dims.index(d)] != n:
+        raise ValueError(f'size mismatch along {d!r}')
+    else:
+      new_dims.append(d)
+      new_shape.append(n)
+
+  for d, n, st in zip(op.outer_dims, op.outer_shape, op.outer_strides):
+    if d in index_maps:
+      tdims, pos = index_maps[d]
+      pos = np.asarray(pos, dtype=np.int64)
+      if pos.size and (pos.min() < 0 or pos.max() >= n):
+        raise IndexError(f'gather positions out of range for {d!r}')
+      terms.append((tuple(tdims), pos * st))
+      for td, tn in zip(tdims, pos.shape):
+        add_dim(td, tn)
+    else:
+      terms.append(((d,), np.arange(n, dtype=np.int64) * st))
+      add_dim(d, n)
+  out = dataclasses.replace(op, outer_dims=tuple(new_dims),
+                            outer_shape=tuple(new_shape),
+                            outer_strides=tuple(0 for _ in new_dims))
+  out.gather_terms = terms
+  return out
+
+
+# ---- weights -----------------------------------------------------------------
+def region_factors(regions: Sequence, latitude: np.ndarray,
+                   longitude: np.ndarray):
+  out = []
+  for r in regions:
+    if r is None:
+      from weatherbench2_b200.regions import RegionFactors  # pylint: disable=import-outside-toplevel
+      out.append(RegionFactors(np.ones(latitude.size), np.ones(longitude.size)))
+    else:
+      out.append(r.factors(latitude, longitude))
+  return out
+
+
+def _segments(factors_along_col: np.ndarray):
+  """Column segments on which every region's factor is constant.
+  factors_along_col: [R, ncol].  Returns (seg_start[nseg+1], seg_w[R, nseg])."""
+  ncol = factors_along_col.shape[1]
+  change = np.any(factors_along_col[:, 1:] != factors_along_col[:, :-1], axis=0)
+  starts = np.concatenate([[0], np.nonzero(change)[0] + 1]).astype(np.int32)
+  seg_start = np.concatenate([starts, [ncol]]).astype(np.int32)
+  seg_w = factors_along_col[:, starts]
+  return seg_start, np.ascontiguousarray(seg_w, dtype=np.float64)
+
+
+def build_weights(ctx: _lib.Context, latitude: np.ndarray,
+                  longitude: np.ndarray, regions: Sequence, layout: str,
+                  row_stride: int, cell_cache: Optional[dict] = None
+                  ) -> list[tuple[list[int], _lib.WeightSpec]]:
+  """WeightSpecs for `regions` (entries may be None = global).
+
+  Regions that carry a 2-D mask (LandRegion) cannot share a launch with a
+  different mask, so the result is a list of (region indices, WeightSpec)
+  groups; regions without a mask all go in the first group.
+  """
+  wlat = lat_weights(latitude)
+  facs = region_factors(regions, latitude, longitude)
+  groups: dict = {}
+  for i, fc in enumerate(facs):
+    key = None if fc.cell is None else fc.cell.tobytes()
+    groups.setdefault(key, []).append(i)
+  out = []
+  nlat, nlon = latitude.size, longitude.size
+  for key, idx in groups.items():
+    for j0 in range(0, len(idx), _lib.MAX_REGIONS):
+      ids = idx[j0:j0 + _lib.MAX_REGIONS]
+      latf = np.stack([facs[i].lat for i in ids])  # [R, nlat]
+      lonf = np.stack([facs[i].lon for i in ids])  # [R, nlon]
+      zero_skip = any(regions[i] is not None for i in ids)
+      cell_dev = None
+      if key is not None:
+        cell = facs[ids[0]].cell
+        cell = cell if layout == 'lat_lon' else cell.T
+        cache_key = (key, layout)
+        if cell_cache is not None and cache_key in cell_cache:
+          cell_dev = cell_cache[cache_key]
+        else:
+          cell_dev = ctx.to_device(np.ascontiguousarray(cell, np.float32))
+          if cell_cache is not None:
+            cell_cache[cache_key] = cell_dev
+      if layout == 'lat_lon':
+        seg_start, seg_w = _segments(lonf)
+        spec = _lib.WeightSpec(nlat, nlon, latf * wlat[None, :], seg_start,
+                               seg_w, None, cell_dev, zero_skip, row_stride)
+      else:
+        seg_start, seg_w = _segments(latf)
+        spec = _lib.WeightSpec(nlon, nlat, lonf, seg_start, seg_w,
+                               wlat.astype(np.float32), cell_dev, zero_skip,
+                               row_stride)
+      out.append((ids, spec))
+  return out
+
+
+# ---- launches ----------------------------------------------------------------
+def _common_base(ops: Sequence[Operand]) -> int:
+  return min(op.addr for op in ops)
+
+
+def run_det_metrics(ctx: _lib.Context, f_ops: Sequence[Operand],
+                    t_ops: Sequence[Operand],
+                    c_ops: Optional[Sequence[Operand]], latitude, longitude,
+                    regions: Sequence, skipna: bool, cell_cache=None):
+  """Runs K1 for a list of variables that share dtype / layout / grid.
+
+  Returns (stats, dims, shapes): stats[v] has shape outer_shape[v] +
+  (len(regions), DET_NSTAT).
+  """
+  nvar = len(f_ops)
+  first = f_ops[0]
+  on_dev = first.on_device
+  dtype_code = _lib.F32 if first.dtype == np.float32 else _lib.F64
+  es = first.itemsize
+  all_ops = list(f_ops) + list(t_ops) + (list(c_ops) if c_ops else [])
+  for op in all_ops:
+    if (op.on_device != on_dev or op.dtype != first.dtype or
+        op.layout != first.layout or op.nrow != first.nrow or
+        op.ncol != first.ncol or op.row_stride != first.row_stride):
+      raise ValueError('operands of one launch must share device, dtype, '
+                       'layout, grid and row stride')
+  base = _common_base(all_ops)
+  dims_list, shape_list, tabs = [], [], [[], [], []]
+  for v in range(nvar):
+    trio = [f_ops[v], t_ops[v]] + ([c_ops[v]] if c_ops else [])
+    dims, shape = broadcast_dims(*trio)
+    dims_list.append(dims)
+    shape_list.append(shape)
+    for k, op in enumerate(trio):
+      rel = (op.addr - base)
+      assert rel % es == 0
+      tabs[k].append(offset_table(op, dims, shape) + rel // es)
+  off_f = np.ascontiguousarray(np.concatenate(tabs[0]))
+  off_t = np.ascontiguousarray(np.concatenate(tabs[1]))
+  off_c = np.ascontiguousarray(np.concatenate(tabs[2])) if c_ops else None
+  nfield = off_f.size
+  nreg = len(regions)
+  result = np.empty((nfield, nreg, _lib.DET_NSTAT), dtype=np.float64)
+  groups = build_weights(ctx, np.asarray(latitude), np.asarray(longitude),
+                         regions, first.layout, first.row_stride, cell_cache)
+  for ids, spec in groups:
+    R = len(ids)
+    if on_dev:
+      out_dev = ctx.malloc(nfield * R * _lib.DET_NSTAT * 8)
+      try:
+        ctx.det_metrics(base, base, base if c_ops else None, dtype_code, off_f,
+                        off_t, off_c, spec, skipna, out_dev)
+        part = ctx.from_device(out_dev, (nfield, R, _lib.DET_NSTAT),
+                               np.float64)
+      finally:
+        ctx.free(out_dev)
+    else:
+      part = np.empty((nfield, R, _lib.DET_NSTAT), dtype=np.float64)
+      ctx.det_metrics(base, base, base if c_ops else None, dtype_code, off_f,
+                      off_t, off_c, spec, skipna, part.ctypes.data, host=True)
+    result[:, ids, :] = part
+  stats, pos = [], 0
+  for v in range(nvar):
+    n = int(np.prod(shape_list[v])) if shape_list[v] else 1
+    stats.append(result[pos:pos + n].reshape(
+        shape_list[v] + (nreg, _lib.DET_NSTAT)))
+    pos += n
+  return stats, dims_list, shape_list
