@@ -275,6 +275,9 @@ def main():
 
   for i in range(args.warmup):
     step(i)
+  _ = out[:args.warmup].sum(dim=0)  # warm the reduction used after the loop
+  if world > 1:
+    dist.all_reduce(_)
   barrier()
   sampler = ClockSampler(local)
   if rank == 0:

@@ -136,6 +136,8 @@ int wb2_destroy(wb2_ctx* c) {
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
   }
   if (c->d_out_tmp) cudaFree(c->d_out_tmp);
+  if (c->tma_partial) cudaFree(c->tma_partial);
+  if (c->scratch) cudaFree(c->scratch);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;

@@ -72,6 +72,12 @@ struct wb2_ctx {
   cudaEvent_t stage_free[2] = {nullptr, nullptr};
   double* d_out_tmp = nullptr;
   size_t out_tmp_cap = 0;
+  // per-(CTA, warp) partials of the TMA-staged K1 kernel
+  double* tma_partial = nullptr;
+  size_t tma_partial_cap = 0;
+  // generic scratch of the other kernels (grown on demand)
+  void* scratch = nullptr;
+  size_t scratch_cap = 0;
 };
 
 namespace wb2 {

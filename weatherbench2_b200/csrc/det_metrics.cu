@@ -347,6 +347,11 @@ static int launch_dtype(wb2_ctx* ctx, const DetParams& p, int64_t nfield, int mo
   }
 }
 
+int det_metrics_tma(wb2_ctx* ctx, bool clim, const void* f, const void* t, const void* c,
+                    int64_t nfield, const int64_t* d_off_f, const int64_t* d_off_t,
+                    const int64_t* d_off_c, const double* d_row_w, const double* d_seg_w,
+                    const wb2_weights* w, int skipna, double* out);
+
 static bool all_multiple(const int64_t* v, int64_t n, int64_t m) {
   if (!v) return true;
   for (int64_t i = 0; i < n; ++i)
@@ -423,6 +428,25 @@ int det_metrics_impl(wb2_ctx* ctx, int mode, const void* f, const void* t, const
   p.rows_per_block = rows_per_block; p.nblk = nblk;
 
   const bool weighted = w->col_w != nullptr || w->cell_w != nullptr;
+
+  // Fast path: TMA-staged persistent kernel (det_tma.cu) when every slab is
+  // 16-byte aligned and the weights are separable with one column segment.
+  // WB2_DET_PATH=ldg forces the LDG kernel (A/B measurements, tests).
+  {
+    const char* force = getenv("WB2_DET_PATH");
+    const bool want_tma = !(force && strcmp(force, "ldg") == 0);
+    if (want_tma && dtype == WB2_F32 && vec_ok && !weighted && w->nseg == 1 &&
+        w->ncol % 4 == 0 && mode != MODE_VECTOR) {
+      int trc = det_metrics_tma(ctx, mode == MODE_CLIM, f, t, c, nfield, p.off_f, p.off_t,
+                                p.off_c, p.row_w, p.seg_w, w, skipna, out);
+      if (trc < 0) return trc;
+      if (trc == 1) {
+        WB2_TRY(pk.release());
+        return WB2_OK;
+      }
+    }
+  }
+
   int rc = dtype == WB2_F32
                ? launch_dtype<float>(ctx, p, nfield, mode, skipna != 0, weighted, vec_ok)
                : launch_dtype<double>(ctx, p, nfield, mode, skipna != 0, weighted, vec_ok);
