@@ -100,9 +100,13 @@ class ExtraTropicalRegion:
 
 @dataclasses.dataclass
 class LandRegion:
-  """regions.py:112-138.  `land_sea_mask` has dims (latitude, longitude)."""
+  """regions.py:112-138.  `land_sea_mask` has dims (latitude, longitude);
+  `latitude` / `longitude` are its coordinate labels (needed only when the
+  region follows a SliceRegion inside a CombinedRegion)."""
   land_sea_mask: np.ndarray
   threshold: Optional[float] = None
+  latitude: Optional[np.ndarray] = None
+  longitude: Optional[np.ndarray] = None
 
 
 @dataclasses.dataclass
@@ -134,6 +138,14 @@ def _region_apply(region, x, w, lat, lon):
     return x, w * region_weights[:, None], lat, lon
   if isinstance(region, LandRegion):
     land = np.asarray(region.land_sea_mask)
+    if region.latitude is not None:
+      # xarray aligns `weights * land_weights` by coordinate label
+      # (regions.py:138); after a SliceRegion the data grid is a subset
+      ilat = np.array([int(np.nonzero(region.latitude == v)[0][0])
+                       for v in lat])
+      ilon = np.array([int(np.nonzero(region.longitude == v)[0][0])
+                       for v in lon])
+      land = land[ilat][:, ilon]
     if land.shape != (lat.size, lon.size):
       raise ValueError("oracle LandRegion needs a full (lat, lon) mask")
     if region.threshold is not None:

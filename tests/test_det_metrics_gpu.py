@@ -310,7 +310,8 @@ def test_land_region_and_combined():
   comb_p = R.CombinedRegion([R.SliceRegion(lat_slice=slice(-30, 60)),
                              R.LandRegion(lsm)])
   comb_o = orc.CombinedRegion([orc.SliceRegion(lat_slice=slice(-30, 60)),
-                               orc.LandRegion(lsm)])
+                               orc.LandRegion(lsm, latitude=lat,
+                                              longitude=lon)])
   got = metrics.MAE().compute_chunk(fds, tds, region=comb_p)['geopotential']
   want, _ = orc.mae(f, fd, t, tdm, lat, lon, region=comb_o)
   np.testing.assert_allclose(got.values, want, rtol=RTOL)

@@ -1,0 +1,250 @@
+"""GPU parity tests for K2 (ensemble metrics) and the energy score against the
+oracle, mirroring weatherbench2/metrics_test.py:192-281, 782-984.
+
+Tolerance: K2 computes in float32 (the reference's data are float32 on disk;
+the mock data here are float64 and get rounded), so 1e-5 relative -- the
+north-star bound -- with an absolute floor for quantities that cancel.
+"""
+import numpy as np
+import pytest
+
+from oracle import wb2_oracle as orc
+import wb2_testdata as td
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _ds(vars_, coords):
+  from weatherbench2_b200 import xarray_lite as xl
+  return xl.Dataset({k: (d, v) for k, (d, v) in vars_.items()}, coords)
+
+
+def _pair(**kw):
+  truth, forecast = td.get_random_truth_and_forecast(**kw)
+  fds = _ds(forecast['vars'], forecast['coords'])
+  tds = _ds(truth['vars'], truth['coords'])
+  lat, lon = truth['coords']['latitude'], truth['coords']['longitude']
+  return fds, tds, forecast, truth, lat, lon
+
+
+def _cmp(got, want, wd, **tol):
+  a, b, _ = orc.align(got.values, got.dims, want, wd)
+  np.testing.assert_allclose(a, b, **tol)
+
+
+@pytest.mark.parametrize('ensemble_size', [2, 3, 5, 7, 10, 17, 33, 50, 64])
+def test_crps_parts_match_oracle(ensemble_size):
+  from weatherbench2_b200 import metrics
+  fds, tds, forecast, truth, lat, lon = _pair(
+      ensemble_size=ensemble_size, lead_stop='2 day', time_stop='2019-12-01T12')
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  args = (f, fd, t, tdm, 'realization', lat, lon)
+  want, wd = orc.crps_skill(*args)
+  _cmp(metrics.CRPSSkill().compute_chunk(fds, tds)['geopotential'], want, wd,
+       rtol=RTOL)
+  want, wd = orc.crps_spread(f, fd, 'realization', lat, lon)
+  _cmp(metrics.CRPSSpread().compute_chunk(fds, tds)['geopotential'], want, wd,
+       rtol=RTOL)
+  want, wd = orc.crps(*args)
+  _cmp(metrics.CRPS().compute_chunk(fds, tds)['geopotential'], want, wd,
+       rtol=RTOL, atol=1e-6)
+  # and against the reference's own brute-force cross-check
+  bf, bd = orc.crps_brute_force(f, fd, t, tdm, 'realization', lat, lon, False)
+  _cmp(metrics.CRPS().compute_chunk(fds, tds)['geopotential'], bf['score'],
+       bd, rtol=RTOL, atol=1e-6)
+  assert metrics.CRPS().compute(fds, tds).attrs['ensemble_size'] == (
+      ensemble_size)
+
+
+def test_ensemble_size_1_gives_mae():
+  """metrics_test.py:210-230."""
+  from weatherbench2_b200 import metrics
+  fds, tds, forecast, truth, lat, lon = _pair(ensemble_size=1)
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  want, wd = orc.crps_skill(f, fd, t, tdm, 'realization', lat, lon)
+  _cmp(metrics.CRPSSkill().compute_chunk(fds, tds)['geopotential'], want, wd,
+       rtol=RTOL)
+  spread = metrics.CRPSSpread().compute_chunk(fds, tds)['geopotential']
+  np.testing.assert_array_equal(spread.values, 0)
+  _cmp(metrics.CRPS().compute_chunk(fds, tds)['geopotential'], want, wd,
+       rtol=RTOL)
+
+
+@pytest.mark.parametrize('skipna', [True, False])
+def test_nan_forecasts(skipna):
+  """metrics_test.py:232-267."""
+  from weatherbench2_b200 import metrics
+  truth, forecast = td.get_random_truth_and_forecast(
+      variables=['geopotential', 'temperature'], ensemble_size=7)
+  fd, f = forecast['vars']['geopotential']
+  f = f.copy()
+  f[(0,) * f.ndim] = np.nan
+  forecast['vars']['geopotential'] = (fd, f)
+  fds = _ds(forecast['vars'], forecast['coords'])
+  tds = _ds(truth['vars'], truth['coords'])
+  lat, lon = truth['coords']['latitude'], truth['coords']['longitude']
+  crps = metrics.CRPS().compute_chunk(fds, tds, skipna=skipna)
+  g = crps['geopotential']
+  idx = tuple(0 for _ in g.dims)
+  sv = g.values.copy()
+  assert np.isnan(sv[idx]) == (not skipna)
+  sv[idx] = 0
+  assert np.all(np.isfinite(sv))
+  assert np.all(np.isfinite(crps['temperature'].values))
+  tdm, t = truth['vars']['geopotential']
+  want, wd = orc.crps(f, fd, t, tdm, 'realization', lat, lon, skipna=skipna)
+  _cmp(g, want, wd, rtol=RTOL, atol=1e-6)
+  for cls, fn in [(metrics.EnsembleMeanMSE, orc.ensemble_mean_mse),
+                  (metrics.DebiasedEnsembleMeanMSE,
+                   orc.debiased_ensemble_mean_mse)]:
+    want, wd = fn(f, fd, t, tdm, 'realization', lat, lon, skipna=skipna)
+    _cmp(cls().compute_chunk(fds, tds, skipna=skipna)['geopotential'], want,
+         wd, rtol=RTOL, atol=1e-6)
+  want, wd = orc.ensemble_variance(f, fd, 'realization', lat, lon,
+                                   skipna=skipna)
+  _cmp(metrics.EnsembleVariance().compute_chunk(
+      fds, tds, skipna=skipna)['geopotential'], want, wd, rtol=RTOL)
+
+
+def test_repeated_forecasts_are_okay():
+  """Ties (metrics_test.py:269-281)."""
+  from weatherbench2_b200 import metrics
+  truth, forecast = td.get_random_truth_and_forecast(ensemble_size=7)
+  fd, f = forecast['vars']['geopotential']
+  f = f.copy()
+  f[0] = f[1]
+  f[3] = f[1]
+  forecast['vars']['geopotential'] = (fd, f)
+  fds = _ds(forecast['vars'], forecast['coords'])
+  tds = _ds(truth['vars'], truth['coords'])
+  lat, lon = truth['coords']['latitude'], truth['coords']['longitude']
+  tdm, t = truth['vars']['geopotential']
+  bf, bd = orc.crps_brute_force(f, fd, t, tdm, 'realization', lat, lon, False)
+  _cmp(metrics.CRPS().compute_chunk(fds, tds)['geopotential'], bf['score'],
+       bd, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize('ensemble_size', [1, 2, 3, 10, 50])
+def test_ensemble_mean_rmse_stddev_variance_debiased(ensemble_size):
+  """metrics_test.py:782-893 (values vs the oracle rather than statistics)."""
+  from weatherbench2_b200 import metrics
+  fds, tds, forecast, truth, lat, lon = _pair(
+      ensemble_size=ensemble_size, lead_stop='3 day')
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  a5 = (f, fd, t, tdm, 'realization', lat, lon)
+  a3 = (f, fd, 'realization', lat, lon)
+  cases = [
+      (metrics.EnsembleMeanRMSESqrtBeforeTimeAvg,
+       orc.ensemble_mean_rmse_sqrt_before_time_avg, a5),
+      (metrics.EnsembleMeanMSE, orc.ensemble_mean_mse, a5),
+      (metrics.EnsembleStddevSqrtBeforeTimeAvg,
+       orc.ensemble_stddev_sqrt_before_time_avg, a3),
+      (metrics.EnsembleVariance, orc.ensemble_variance, a3),
+  ]
+  if ensemble_size > 1:
+    cases.append((metrics.DebiasedEnsembleMeanMSE,
+                  orc.debiased_ensemble_mean_mse, a5))
+  for cls, fn, args in cases:
+    got = cls().compute_chunk(fds, tds)['geopotential']
+    want, wd = fn(*args)
+    assert set(got.dims) == {'prediction_timedelta', 'time', 'level'}
+    _cmp(got, want, wd, rtol=RTOL, atol=1e-6)
+  if ensemble_size == 1:
+    np.testing.assert_array_equal(
+        metrics.EnsembleStddevSqrtBeforeTimeAvg().compute_chunk(
+            fds, tds)['geopotential'].values, 0)
+    deb = metrics.DebiasedEnsembleMeanMSE().compute_chunk(fds, tds)
+    assert np.isnan(deb['geopotential'].values).all()
+
+
+def test_effect_of_large_bias_and_perfect_prediction():
+  """metrics_test.py:833-851."""
+  from weatherbench2_b200 import metrics, xarray_lite as xl
+  truth, forecast = td.get_random_truth_and_forecast(ensemble_size=10)
+  tdm, t = truth['vars']['geopotential']
+  truth['vars']['geopotential'] = (tdm, t + 1000)
+  fds = _ds(forecast['vars'], forecast['coords'])
+  tds = _ds(truth['vars'], truth['coords'])
+  rmse = metrics.EnsembleMeanRMSESqrtBeforeTimeAvg().compute_chunk(fds, tds)
+  np.testing.assert_allclose(1000, rmse['geopotential'].values.mean(),
+                             rtol=1e-3)
+  perfect = xl.Dataset(
+      {'geopotential': (('realization',) + tdm, (t + 1000)[None])},
+      dict(truth['coords'], realization=np.arange(1)))
+  rmse = metrics.EnsembleMeanRMSESqrtBeforeTimeAvg().compute_chunk(perfect,
+                                                                   tds)
+  np.testing.assert_allclose(rmse['geopotential'].values, 0, atol=1e-6)
+
+
+@pytest.mark.parametrize('ensemble_size', [1, 2, 3, 10])
+def test_energy_score(ensemble_size):
+  """metrics_test.py:923-984."""
+  from weatherbench2_b200 import metrics
+  fds, tds, forecast, truth, lat, lon = _pair(ensemble_size=ensemble_size,
+                                              lead_stop='3 day')
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  a5 = (f, fd, t, tdm, 'realization', lat, lon)
+  score = metrics.EnergyScore().compute_chunk(fds, tds)['geopotential']
+  spread = metrics.EnergyScoreSpread().compute_chunk(fds, tds)['geopotential']
+  skill = metrics.EnergyScoreSkill().compute_chunk(fds, tds)['geopotential']
+  for da in (score, spread, skill):
+    assert set(da.dims) == {'prediction_timedelta', 'time', 'level'}
+  want, wd = orc.energy_score_skill(*a5)
+  _cmp(skill, want, wd, rtol=2e-6)
+  want, wd = orc.energy_score_spread(f, fd, 'realization', lat, lon)
+  _cmp(spread, want, wd, rtol=2e-6)
+  want, wd = orc.energy_score(*a5)
+  _cmp(score, want, wd, rtol=2e-6, atol=1e-6)
+  if ensemble_size == 1:
+    np.testing.assert_array_equal(spread.values, 0)
+
+
+def test_regions_lon_lat_layout_and_device_inputs():
+  """K2 with several regions (incl. a land mask) in one pass, and with the
+  ensemble resident on the device."""
+  import torch
+  from weatherbench2_b200 import metrics, regions as R, xarray_lite as xl
+  fds, tds, forecast, truth, lat, lon = _pair(
+      ensemble_size=5, spatial_resolution_in_degrees=10, lead_stop='1 day')
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  rs = np.random.RandomState(1)
+  lsm = (rs.rand(lat.size, lon.size) > 0.4).astype(float)
+  preg = [None, R.SliceRegion(lat_slice=slice(-20, 20)),
+          R.ExtraTropicalRegion(), R.LandRegion(lsm),
+          R.SliceRegion(lon_slice=[slice(300, None), slice(0, 60)])]
+  oreg = [None, orc.SliceRegion(lat_slice=slice(-20, 20)),
+          orc.ExtraTropicalRegion(), orc.LandRegion(lsm),
+          orc.SliceRegion(lon_slice=[slice(300, None), slice(0, 60)])]
+  dev_f = xl.Dataset({'geopotential': (fd, torch.from_numpy(
+      f.astype(np.float32)).cuda())}, forecast['coords'])
+  dev_t = xl.Dataset({'geopotential': (tdm, torch.from_numpy(
+      t.astype(np.float32)).cuda())}, truth['coords'])
+  with metrics.batch(preg):
+    for p, o in zip(preg, oreg):
+      want, wd = orc.crps(f, fd, t, tdm, 'realization', lat, lon, region=o)
+      _cmp(metrics.CRPS().compute_chunk(fds, tds, region=p)['geopotential'],
+           want, wd, rtol=RTOL, atol=1e-6)
+      _cmp(metrics.CRPS().compute_chunk(dev_f, dev_t,
+                                        region=p)['geopotential'],
+           want, wd, rtol=RTOL, atol=1e-6)
+
+
+def test_too_many_members_raises_loudly():
+  from weatherbench2_b200 import _lib, metrics
+  fds, tds, *_ = _pair(ensemble_size=65, lead_stop='0 day',
+                       time_stop='2019-12-01T03')
+  with pytest.raises(_lib.Wb2Error):
+    metrics.CRPS().compute_chunk(fds, tds)
+
+
+def test_missing_ensemble_dim_raises():
+  from weatherbench2_b200 import metrics
+  fds, tds, *_ = _pair(ensemble_size=None)
+  with pytest.raises(ValueError):
+    metrics.CRPS().compute_chunk(fds, tds)

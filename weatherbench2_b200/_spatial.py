@@ -379,3 +379,96 @@ def run_det_metrics(ctx: _lib.Context, f_ops: Sequence[Operand],
         shape_list[v] + (nreg, _lib.DET_NSTAT)))
     pos += n
   return stats, dims_list, shape_list
+
+
+# ---- K2: ensemble metrics ----------------------------------------------------
+def split_member_dim(op: Operand, ens_dim: str):
+  """Removes `ens_dim` from the outer dims of `op`; returns (op', M, stride)."""
+  if ens_dim not in op.outer_dims:
+    raise ValueError(f'ensemble_dim={ens_dim!r} not found in {op.outer_dims}')
+  i = op.outer_dims.index(ens_dim)
+  m, stride = op.outer_shape[i], op.outer_strides[i]
+  keep = [k for k in range(len(op.outer_dims)) if k != i]
+  out = dataclasses.replace(
+      op, outer_dims=tuple(op.outer_dims[k] for k in keep),
+      outer_shape=tuple(op.outer_shape[k] for k in keep),
+      outer_strides=tuple(op.outer_strides[k] for k in keep))
+  return out, int(m), int(stride)
+
+
+def _to_device_operand(ctx: _lib.Context, op: Operand, staged: list) -> Operand:
+  """Uploads a host operand's backing array (same strides) to the device."""
+  if op.on_device:
+    return op
+  arr = op.data
+  base = arr
+  while isinstance(base, np.ndarray) and base.base is not None and isinstance(
+      base.base, np.ndarray):
+    base = base.base
+  # upload the smallest contiguous span that covers the view
+  lo = arr.ctypes.data
+  span = 1 + sum((n - 1) * abs(s) for n, s in zip(arr.shape, arr.strides)
+                 ) // arr.itemsize if arr.size else 1
+  flat = np.ctypeslib.as_array(
+      (np.ctypeslib.ctypes.c_char * (span * arr.itemsize)).from_address(lo))
+  dptr = ctx.to_device(flat)
+  staged.append(dptr)
+  out = dataclasses.replace(op, addr=dptr, on_device=True)
+  if hasattr(op, 'gather_terms'):
+    out.gather_terms = op.gather_terms
+  return out
+
+
+def run_ens_metrics(ctx: _lib.Context, x_ops: Sequence[Operand],
+                    t_ops: Sequence[Operand], ens_dim: str, latitude,
+                    longitude, regions: Sequence, skipna: bool,
+                    cell_cache=None):
+  """Runs K2 for variables sharing layout / grid.  Returns (stats, dims,
+  shapes, M): stats[v] has shape outer_shape[v] + (len(regions), ENS_NSTAT)."""
+  staged: list = []
+  try:
+    xs, ts, ms, strides = [], [], [], []
+    for xo, to in zip(x_ops, t_ops):
+      if ens_dim in to.outer_dims:
+        raise ValueError(f'truth must not have the {ens_dim!r} dimension')
+      xo = _to_device_operand(ctx, xo, staged)
+      to = _to_device_operand(ctx, to, staged)
+      xo, m, st = split_member_dim(xo, ens_dim)
+      xs.append(xo)
+      ts.append(to)
+      ms.append(m)
+      strides.append(st)
+    first = xs[0]
+    nreg = len(regions)
+    groups = build_weights(ctx, np.asarray(latitude), np.asarray(longitude),
+                           regions, first.layout, first.row_stride, cell_cache)
+    stats, dims_list, shape_list = [], [], []
+    for xo, to, m, st in zip(xs, ts, ms, strides):
+      if (to.layout != xo.layout or to.row_stride != xo.row_stride or
+          to.nrow != xo.nrow or to.ncol != xo.ncol):
+        raise ValueError('forecast and truth must share layout and grid')
+      # xarray puts truth's dims first for abs(truth - forecast)
+      # (metrics.py:824); we keep the forecast-first order used by every other
+      # metric of this module and of the reference's `mean/var` based ones.
+      dims, shape = broadcast_dims(xo, to)
+      base = min(xo.addr, to.addr)
+      off_x = offset_table(xo, dims, shape) + (xo.addr - base) // 4
+      off_t = offset_table(to, dims, shape) + (to.addr - base) // 4
+      nfield = off_x.size
+      res = np.empty((nfield, nreg, _lib.ENS_NSTAT), dtype=np.float64)
+      for ids, spec in groups:
+        out_dev = ctx.malloc(nfield * len(ids) * _lib.ENS_NSTAT * 8)
+        try:
+          ctx.ens_metrics(base, base, _lib.F32, m, st, off_x, off_t, spec,
+                          skipna, out_dev)
+          res[:, ids, :] = ctx.from_device(
+              out_dev, (nfield, len(ids), _lib.ENS_NSTAT), np.float64)
+        finally:
+          ctx.free(out_dev)
+      stats.append(res.reshape(shape + (nreg, _lib.ENS_NSTAT)))
+      dims_list.append(dims)
+      shape_list.append(shape)
+    return stats, dims_list, shape_list, ms
+  finally:
+    for p in staged:
+      ctx.free(p)

@@ -6,16 +6,19 @@
 // UBLKCP) into a ring of stages guarded by full/empty mbarriers, so the number
 // of bytes in flight per SM (~140 KB) no longer depends on registers or
 // occupancy.  One persistent CTA per SM:
-//   warp 8   : producer -- one elected lane walks the CTA's tile list and
-//              issues 2 or 3 bulk copies per tile (forecast, truth[, clim]);
-//   warps 0-7: consumers -- warp w owns stages w, w+8, ...; it reads its tile
-//              with conflict-free LDS.128, accumulates the unweighted f32
-//              sums, releases the stage, butterfly-reduces and lets lane r add
-//              region r's float64 weight * sums to its accumulators.
-// A tile is a 16-byte-aligned chunk of one row (about 3 KB per operand).  Tiles
-// are dealt to CTAs in contiguous ranges, so a CTA touches few fields; every
-// (CTA, warp) writes float64 partials per touched field and a finalize kernel
-// adds them in a fixed order (deterministic).
+//   warp 8   : producer -- one elected lane walks the CTA's tile list (32-bit
+//              incremental index math only) and issues 2 or 3 bulk copies per
+//              tile (forecast, truth[, clim]);
+//   warps 0-7: consumers -- warp pair q = w/2 owns tiles q, q+4, ...; each warp
+//              of the pair reads one half of the tile with conflict-free
+//              LDS.128, accumulates the unweighted f32 sums, releases the
+//              stage, butterfly-reduces and lets lane r add region r's float64
+//              weight * sums to its accumulators.
+// A tile is one whole row (5760 B per operand at 1440 columns), so the producer
+// issues one tile per ~750 cycles at full HBM rate.  Tiles are dealt to CTAs in
+// contiguous ranges, so a CTA touches few fields; every (CTA, warp) writes
+// float64 partials per touched field and a finalize kernel adds them in a
+// fixed order (deterministic).
 //
 // Eligibility (checked by the caller): float32, every slab 16-byte aligned
 // (offsets, row stride and ncol multiples of 4 elements), one column segment,
@@ -26,6 +29,7 @@ namespace wb2 {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;
+constexpr int kTilesInFlight = kConsumerWarps / 2;  // tiles being consumed at once
 
 struct TmaParams {
   const float* f;
@@ -42,10 +46,8 @@ struct TmaParams {
   int64_t row_stride;
   int32_t nregion;
   int32_t zero_skip;
-  int32_t nchunk;           // chunks per row
-  int32_t chunk;            // elements per chunk (multiple of 4)
-  int32_t tiles_per_field;  // nrow * nchunk
-  int32_t nstage;           // multiple of kConsumerWarps
+  int32_t tiles_per_field;  // = nrow (one tile per row)
+  int32_t nstage;           // multiple of kTilesInFlight
   int32_t stage_op_bytes;   // bytes reserved per operand per stage (128-B mult.)
   int32_t maxslots;
 };
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
   if (threadIdx.x == 0) {
     for (int s = 0; s < nstage; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);  // both warps of the consuming pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -155,32 +157,32 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
   if (warp == kConsumerWarps) {
     // ------------------------------ producer --------------------------------
     if (lane == 0) {
-      int64_t cur_field = -1;
-      const float *pf = nullptr, *pt = nullptr, *pc = nullptr;
+      int64_t field = first_field;
+      int row = static_cast<int>(t0 - first_field * p.tiles_per_field);
+      const float* pf = p.f + p.off_f[field];
+      const float* pt = p.t + p.off_t[field];
+      const float* pc = CLIM ? p.c + p.off_c[field] : nullptr;
+      const uint32_t bytes = static_cast<uint32_t>(p.ncol) * 4u;
+      int s = 0;
+      uint32_t use = 0;
       for (int64_t j = 0; j < ncta_tiles; ++j) {
-        const int64_t tile = t0 + j;
-        const int64_t field = tile / p.tiles_per_field;
-        const int rem = static_cast<int>(tile - field * p.tiles_per_field);
-        const int row = rem / p.nchunk;
-        const int ck = rem - row * p.nchunk;
-        if (field != cur_field) {
-          cur_field = field;
-          pf = p.f + p.off_f[field];
-          pt = p.t + p.off_t[field];
-          if (CLIM) pc = p.c + p.off_c[field];
-        }
-        const int s = static_cast<int>(j % nstage);
-        const uint32_t use = static_cast<uint32_t>(j / nstage);
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
-        const int col0 = ck * p.chunk;
-        const int len = min(p.chunk, p.ncol - col0);
-        const uint32_t bytes = static_cast<uint32_t>(len) * 4u;
-        const int64_t e = int64_t(row) * p.row_stride + col0;
+        const int64_t e = int64_t(row) * p.row_stride;
         unsigned char* dst = smem + stage_bytes * s;
         mbar_arrive_expect_tx(&full[s], bytes * NOPER);
         tma_load_1d(dst, pf + e, bytes, &full[s]);
         tma_load_1d(dst + p.stage_op_bytes, pt + e, bytes, &full[s]);
         if (CLIM) tma_load_1d(dst + 2 * p.stage_op_bytes, pc + e, bytes, &full[s]);
+        if (++s == nstage) { s = 0; ++use; }
+        if (++row == p.nrow) {
+          row = 0;
+          ++field;
+          if (j + 1 < ncta_tiles) {
+            pf = p.f + p.off_f[field];
+            pt = p.t + p.off_t[field];
+            if (CLIM) pc = p.c + p.off_c[field];
+          }
+        }
       }
     }
     return;
@@ -222,12 +224,16 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
     for (int i = 0; i <= NS; ++i) accd[i] = 0.0;
   };
 
-  for (int64_t j = warp; j < ncta_tiles; j += kConsumerWarps) {
-    const int64_t tile = t0 + j;
-    const int64_t field = tile / p.tiles_per_field;
-    const int rem = static_cast<int>(tile - field * p.tiles_per_field);
-    const int row = rem / p.nchunk;
-    const int ck = rem - row * p.nchunk;
+  const int pair = warp >> 1, half = warp & 1;
+  const int n4 = p.ncol >> 2;
+  const int n4a = (n4 + 1) >> 1;
+  const int i0 = half ? n4a : 0, i1 = half ? n4 : n4a;
+  int64_t field = first_field;
+  int row = static_cast<int>(t0 - first_field * p.tiles_per_field) + pair;
+  int s = pair;
+  uint32_t use = 0;
+  for (int64_t j = pair; j < ncta_tiles; j += kTilesInFlight) {
+    while (row >= p.nrow) { row -= p.nrow; ++field; }
     if (field != cur_field) {
       flush_field(cur_field);
       cur_field = field;
@@ -236,10 +242,6 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
     double w = 0.0;
     if (lane < R) w = p.row_w[int64_t(lane) * p.nrow + row] * p.seg_w[lane];
 
-    const int s = static_cast<int>(j % nstage);
-    const uint32_t use = static_cast<uint32_t>(j / nstage);
-    const int col0 = ck * p.chunk;
-    const int n4 = min(p.chunk, p.ncol - col0) >> 2;
     const unsigned char* src = smem + stage_bytes * s;
     const float4* sf = reinterpret_cast<const float4*>(src);
     const float4* st = reinterpret_cast<const float4*>(src + p.stage_op_bytes);
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
 
     mbar_wait(&full[s], use & 1);
 #pragma unroll 2
-    for (int i = lane; i < n4; i += 32) {
+    for (int i = i0 + lane; i < i1; i += 32) {
       const float4 a = sf[i];
       const float4 bq = st[i];
       float4 cq = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -262,15 +264,18 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
       tma_cell<CLIM, SKIPNA>(a.w, bq.w, cq.w, acc);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);  // stage may be refilled
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
 
 #pragma unroll
     for (int i = 0; i < NS; ++i) acc[i] = warp_sum(acc[i]);
     if (lane < R && !(zero_skip && w == 0.0)) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) accd[i] += w * double(acc[i]);
-      if (!SKIPNA) accd[NS] += w * double(n4 * 4);
+      if (!SKIPNA) accd[NS] += w * double((i1 - i0) * 4);
     }
+    row += kTilesInFlight;
+    s += kTilesInFlight;
+    if (s >= nstage) { s -= nstage; ++use; }
   }
   flush_field(cur_field);
 }
@@ -302,16 +307,12 @@ int det_metrics_tma(wb2_ctx* ctx, bool clim, const void* f, const void* t, const
                     const wb2_weights* w, int skipna, double* out) {
   const int noper = clim ? 3 : 2;
   if (w->ncol * 4 < 512) return 0;
-  // chunks of about 2880 B per operand (half a 1440-column row)
-  int nchunk = (w->ncol * 4 + 2879) / 2880;
-  int chunk = ((w->ncol + nchunk - 1) / nchunk + 3) / 4 * 4;
-  nchunk = (w->ncol + chunk - 1) / chunk;
-  const int stage_op_bytes = (chunk * 4 + 127) / 128 * 128;
+  const int stage_op_bytes = (w->ncol * 4 + 127) / 128 * 128;
   const size_t budget = 220 * 1024;  // of the 227 KB a CTA may use on sm_100
   int nstage = static_cast<int>(budget / (size_t(noper) * stage_op_bytes));
-  nstage = nstage / kConsumerWarps * kConsumerWarps;
+  nstage = nstage / kTilesInFlight * kTilesInFlight;
   if (nstage > 32) nstage = 32;
-  if (nstage < 2 * kConsumerWarps) return 0;
+  if (nstage < 2 * kTilesInFlight) return 0;
   const size_t smem = size_t(nstage) * noper * stage_op_bytes + 2 * nstage * sizeof(uint64_t);
 
   TmaParams p;
@@ -322,7 +323,7 @@ int det_metrics_tma(wb2_ctx* ctx, bool clim, const void* f, const void* t, const
   p.row_w = d_row_w; p.seg_w = d_seg_w;
   p.nrow = w->nrow; p.ncol = w->ncol; p.row_stride = w->row_stride;
   p.nregion = w->nregion; p.zero_skip = w->zero_skip;
-  p.nchunk = nchunk; p.chunk = chunk; p.tiles_per_field = w->nrow * nchunk;
+  p.tiles_per_field = w->nrow;
   p.ntiles = nfield * p.tiles_per_field;
   p.nstage = nstage; p.stage_op_bytes = stage_op_bytes;
   int ncta = ctx->num_sms;

@@ -1,0 +1,335 @@
+// K2 -- fused ensemble metrics (sm_100a).
+//
+// One read of the M members (+ truth) of every grid point yields the five
+// point-wise quantities behind CRPS / CRPSSkill / CRPSSpread
+// (weatherbench2/metrics.py:657-715, 781-846), EnsembleMeanMSE / RMSE
+// (:1293-1333), EnsembleVariance / Stddev (:1185-1241) and
+// DebiasedEnsembleMeanMSE (:532-565, :1347-1363), which are then reduced over
+// latitude x longitude with the same weight machinery as K1:
+//   [0] skill_pt  = mean_m |t - x_m|                          (metrics.py:824)
+//   [1] spread_pt = 2 * mean_m((2 r_m - M - 1) x_m) / (M - 1) (metrics.py:805-813)
+//   [2] (t - xbar)^2          [3] var_m(x, ddof=1)     [4] [2] - [3] / M
+// The reference ranks with np.argsort + put_along_axis on an int64 copy of the
+// whole ensemble (:836-846); here the members of a point sit in registers and
+// go through a Batcher sorting network (sort_networks.inc), after which
+// sum_i (2 i - M - 1) x_(i) is the same quantity (ties do not matter).
+//
+// Roofline: (4 M + 4) bytes per grid point from HBM; the sorting network is
+// ~2 * 403 FMNMX per point at M = 50, which puts this kernel near the
+// ALU-pipe / HBM ridge.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace wb2 {
+
+#define CE(a, b)                          \
+  {                                       \
+    const float lo_ = fminf(v[a], v[b]);  \
+    const float hi_ = fmaxf(v[a], v[b]);  \
+    v[a] = lo_;                           \
+    v[b] = hi_;                           \
+  }
+#include "sort_networks.inc"
+#undef CE
+
+constexpr int kEnsWarps = 4;
+constexpr int kEnsThreads = kEnsWarps * 32;
+constexpr int kEnsStats = 5;
+
+struct EnsParams {
+  const float* x;
+  const float* t;
+  const int64_t* off_x;
+  const int64_t* off_t;
+  const double* row_w;       // [R][nrow]
+  const int32_t* seg_start;  // [nseg + 1]
+  const double* seg_w;       // [R][nseg]
+  const float* col_w;        // [ncol] or null
+  const float* cell_w;       // [nrow][ncol] or null
+  double* partial;           // [nfield][nblk][R][WB2_ENS_NSTAT]
+  int64_t member_stride;
+  int64_t row_stride;
+  int32_t nmember;
+  int32_t nrow, ncol;
+  int32_t nregion, nseg;
+  int32_t zero_skip;
+  int32_t rows_per_block;
+  int32_t nblk;
+};
+
+// Point-wise statistics of one grid point.  x[m] for m >= M is padding.
+template <int MP, bool SKIPNA, bool EXACT>
+__device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float (&val)[kEnsStats]) {
+  const float nanf_ = __int_as_float(0x7fc00000);
+  const float inf_ = __int_as_float(0x7f800000);
+  float sumx = 0.f, suma = 0.f;
+  float nvalid = 0.f, navalid = 0.f;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (EXACT || m < M) {
+      const float xm = v[m];
+      const float a = fabsf(t - xm);  // metrics.py:824
+      if (SKIPNA) {
+        if (xm == xm) { sumx += xm; nvalid += 1.f; }
+        if (a == a) { suma += a; navalid += 1.f; }
+      } else {
+        sumx += xm;
+        suma += a;
+      }
+    }
+  }
+  const float fm = float(M);
+  const float mean = SKIPNA ? sumx / nvalid : sumx / fm;  // 0/0 -> NaN like nanmean
+  float ss = 0.f;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (EXACT || m < M) {
+      const float dx = v[m] - mean;
+      if (SKIPNA) {
+        if (dx == dx) ss += dx * dx;
+      } else {
+        ss += dx * dx;
+      }
+    }
+  }
+  float var;
+  if (SKIPNA) var = nvalid > 1.f ? ss / (nvalid - 1.f) : nanf_;  // np.nanvar(ddof=1)
+  else var = ss / (fm - 1.f);                                    // M == 1 -> 0/0 = NaN
+  const float dm = t - mean;
+  const float mse = dm * dm;
+  val[0] = SKIPNA ? suma / navalid : suma / fm;
+  val[2] = mse;
+  val[3] = var;
+  val[4] = mse - var / fm;  // metrics.py:564-565 (always divides by the full M)
+
+  // ---- spread: ranks via sorting network (metrics.py:804-813) ---------------
+  if (M < 2) {
+    val[1] = 0.f;  // metrics.py:788-789
+    return;
+  }
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    if (!EXACT && m >= M) v[m] = inf_;          // padding sorts last
+    else if (SKIPNA && !(v[m] == v[m])) v[m] = inf_;  // NaN sorts last (np.argsort)
+  }
+  SortNet<MP>::run(v);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MP; ++i) {
+    // coefficient 2 r - M - 1 with r = i + 1
+    const float coef = float(2 * (i + 1)) - fm - 1.f;
+    if (SKIPNA) {
+      if (float(i) < nvalid) s += coef * v[i];
+    } else if (EXACT || i < M) {
+      s += coef * v[i];
+    }
+  }
+  float spread = SKIPNA ? 2.f * (s / nvalid) / (fm - 1.f) : 2.f * (s / fm) / (fm - 1.f);
+  if (!SKIPNA && !(sumx == sumx)) spread = nanf_;  // a NaN member poisons the point
+  val[1] = spread;
+}
+
+template <int MP, bool SKIPNA, bool EXACT>
+__global__ void __launch_bounds__(kEnsThreads, 4) ens_metrics_kernel(const EnsParams p) {
+  constexpr int NCNT = SKIPNA ? kEnsStats : 1;
+  constexpr int NS = kEnsStats + NCNT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* red = reinterpret_cast<double*>(smem_raw);                    // [warps][32][NS]
+  float* s_colw = reinterpret_cast<float*>(red + kEnsWarps * 32 * NS);  // [ncol]
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t field = blockIdx.x / p.nblk;
+  const int blk = blockIdx.x % p.nblk;
+  const int R = p.nregion;
+  const int M = p.nmember;
+  const bool weighted = p.col_w != nullptr || p.cell_w != nullptr;
+  if (p.col_w) {
+    for (int i = threadIdx.x; i < p.ncol; i += kEnsThreads) s_colw[i] = p.col_w[i];
+    __syncthreads();
+  }
+  const float* __restrict__ px = p.x + p.off_x[field];
+  const float* __restrict__ pt = p.t + p.off_t[field];
+  const bool zero_skip = p.zero_skip != 0;
+
+  double accd[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) accd[i] = 0.0;
+
+  const int row0 = blk * p.rows_per_block;
+  const int row1 = min(p.nrow, row0 + p.rows_per_block);
+  for (int row = row0 + warp; row < row1; row += kEnsWarps) {
+    const int64_t rbase = int64_t(row) * p.row_stride;
+    for (int k = 0; k < p.nseg; ++k) {
+      const int s = p.seg_start[k];
+      const int e = p.seg_start[k + 1];
+      float acc[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[i] = 0.f;
+      for (int col = s + lane; col < e; col += 32) {
+        float v[MP];
+        const float* src = px + rbase + col;
+#pragma unroll
+        for (int m = 0; m < MP; ++m) {
+          if (EXACT || m < M) v[m] = ldg_stream(src + int64_t(m) * p.member_stride);
+          else v[m] = 0.f;
+        }
+        const float t = ldg_stream(pt + rbase + col);
+        float wc = 1.f;
+        if (weighted) {
+          if (p.col_w) wc *= s_colw[col];
+          if (p.cell_w) wc *= p.cell_w[int64_t(row) * p.ncol + col];
+          if (zero_skip && wc == 0.f) continue;  // metrics.py:160
+        }
+        float val[kEnsStats];
+        ens_point<MP, SKIPNA, EXACT>(v, t, M, val);
+#pragma unroll
+        for (int i = 0; i < kEnsStats; ++i) {
+          if (SKIPNA) {
+            if (val[i] == val[i]) {
+              acc[i] += wc * val[i];
+              acc[kEnsStats + i] += wc;
+            }
+          } else {
+            acc[i] += wc * val[i];
+          }
+        }
+        if (!SKIPNA) acc[kEnsStats] += wc;
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) acc[i] = warp_sum(acc[i]);
+      if (lane < R) {
+        const double w = p.row_w[int64_t(lane) * p.nrow + row] * p.seg_w[lane * p.nseg + k];
+        if (!(zero_skip && w == 0.0)) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) accd[i] += w * double(acc[i]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < NS; ++i) red[(warp * 32 + lane) * NS + i] = accd[i];
+  __syncthreads();
+  double* out = p.partial + (field * p.nblk + blk) * int64_t(R) * WB2_ENS_NSTAT;
+  for (int idx = threadIdx.x; idx < R * WB2_ENS_NSTAT; idx += kEnsThreads) {
+    const int r = idx / WB2_ENS_NSTAT;
+    const int st = idx % WB2_ENS_NSTAT;
+    const int slot = st < kEnsStats ? st : kEnsStats + (SKIPNA ? st - kEnsStats : 0);
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kEnsWarps; ++w) v += red[(w * 32 + r) * NS + slot];
+    out[idx] = v;
+  }
+}
+
+__global__ void ens_finalize_kernel(const double* __restrict__ partial, double* __restrict__ out,
+                                    int nblk, int per_field) {
+  const int64_t field = blockIdx.x;
+  for (int i = threadIdx.x; i < per_field; i += blockDim.x) {
+    const double* src = partial + field * int64_t(nblk) * per_field + i;
+    double v = 0.0;
+    for (int b = 0; b < nblk; ++b) v += src[int64_t(b) * per_field];
+    out[field * per_field + i] = v;
+  }
+}
+
+template <int MP>
+static int launch_ens(wb2_ctx* ctx, const EnsParams& p, int64_t nfield, bool skipna) {
+  const bool exact = p.nmember == MP;
+  const int ns = kEnsStats + (skipna ? kEnsStats : 1);
+  const size_t smem = size_t(kEnsWarps) * 32 * ns * sizeof(double) +
+                      (p.col_w ? size_t(p.ncol) * sizeof(float) : 0);
+  dim3 grid(static_cast<unsigned>(nfield * p.nblk));
+  auto go = [&](auto kernel) -> int {
+    if (smem > 48 * 1024)
+      WB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    kernel<<<grid, kEnsThreads, smem, ctx->stream>>>(p);
+    WB2_CUDA_TRY(cudaGetLastError());
+    return WB2_OK;
+  };
+  if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true>)
+                           : go(ens_metrics_kernel<MP, true, false>);
+  return exact ? go(ens_metrics_kernel<MP, false, true>)
+               : go(ens_metrics_kernel<MP, false, false>);
+}
+
+}  // namespace wb2
+
+using namespace wb2;
+
+extern "C" int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                               int32_t nmember, int64_t member_stride, int64_t nfield,
+                               const int64_t* off_x, const int64_t* off_t,
+                               const wb2_weights* w, int skipna, double* out) {
+  WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
+  WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_metrics: only WB2_F32 inputs are supported");
+  WB2_REQUIRE(nmember >= 1, "wb2_ens_metrics: nmember must be >= 1");
+  WB2_REQUIRE(nmember <= 64,
+              "wb2_ens_metrics: at most 64 ensemble members are supported (got %d)", nmember);
+  WB2_TRY(validate_weights(w));
+  WB2_REQUIRE(out != nullptr, "out is NULL");
+  WB2_REQUIRE(nfield >= 0 && nfield <= (int64_t(1) << 24), "nfield out of range");
+  if (nfield == 0) return WB2_OK;
+  WB2_REQUIRE(x && t && off_x && off_t, "x/t and their offset tables must not be NULL");
+  DeviceGuard guard(ctx->device);
+
+  int rows_per_block = 2 * kEnsWarps;
+  int nblk = (w->nrow + rows_per_block - 1) / rows_per_block;
+  while (nblk * nfield < 4 * ctx->num_sms && rows_per_block > kEnsWarps) {
+    rows_per_block /= 2;
+    nblk = (w->nrow + rows_per_block - 1) / rows_per_block;
+  }
+  const int R = w->nregion;
+  const size_t per_field = size_t(R) * WB2_ENS_NSTAT;
+  Packer pk(ctx);
+  size_t o_x = pk.add(off_x, nfield * sizeof(int64_t));
+  size_t o_t = pk.add(off_t, nfield * sizeof(int64_t));
+  size_t o_rw = pk.add(w->row_w, size_t(R) * w->nrow * sizeof(double));
+  size_t o_ss = pk.add(w->seg_start, size_t(w->nseg + 1) * sizeof(int32_t));
+  size_t o_sw = pk.add(w->seg_w, size_t(R) * w->nseg * sizeof(double));
+  size_t o_cw = w->col_w ? pk.add(w->col_w, size_t(w->ncol) * sizeof(float)) : 0;
+  size_t o_part = pk.reserve(size_t(nfield) * nblk * per_field * sizeof(double));
+  WB2_TRY(pk.commit());
+
+  EnsParams p;
+  p.x = static_cast<const float*>(x);
+  p.t = static_cast<const float*>(t);
+  p.off_x = pk.dev<int64_t>(o_x);
+  p.off_t = pk.dev<int64_t>(o_t);
+  p.row_w = pk.dev<double>(o_rw);
+  p.seg_start = pk.dev<int32_t>(o_ss);
+  p.seg_w = pk.dev<double>(o_sw);
+  p.col_w = w->col_w ? pk.dev<float>(o_cw) : nullptr;
+  p.cell_w = w->cell_w;
+  p.partial = pk.dev<double>(o_part);
+  p.member_stride = member_stride;
+  p.row_stride = w->row_stride;
+  p.nmember = nmember;
+  p.nrow = w->nrow; p.ncol = w->ncol;
+  p.nregion = R; p.nseg = w->nseg; p.zero_skip = w->zero_skip;
+  p.rows_per_block = rows_per_block; p.nblk = nblk;
+
+  int rc;
+  const bool sk = skipna != 0;
+  if (nmember <= 2) rc = launch_ens<2>(ctx, p, nfield, sk);
+  else if (nmember <= 3) rc = launch_ens<3>(ctx, p, nfield, sk);
+  else if (nmember <= 4) rc = launch_ens<4>(ctx, p, nfield, sk);
+  else if (nmember <= 5) rc = launch_ens<5>(ctx, p, nfield, sk);
+  else if (nmember <= 8) rc = launch_ens<8>(ctx, p, nfield, sk);
+  else if (nmember <= 10) rc = launch_ens<10>(ctx, p, nfield, sk);
+  else if (nmember <= 16) rc = launch_ens<16>(ctx, p, nfield, sk);
+  else if (nmember <= 20) rc = launch_ens<20>(ctx, p, nfield, sk);
+  else if (nmember <= 32) rc = launch_ens<32>(ctx, p, nfield, sk);
+  else if (nmember <= 50) rc = launch_ens<50>(ctx, p, nfield, sk);
+  else rc = launch_ens<64>(ctx, p, nfield, sk);
+  if (rc != WB2_OK) return rc;
+  ens_finalize_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
+      p.partial, out, nblk, static_cast<int>(per_field));
+  WB2_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 2;
+  WB2_TRY(pk.release());
+  return WB2_OK;
+}

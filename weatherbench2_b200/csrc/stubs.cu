@@ -2,11 +2,6 @@
 #include "common.cuh"
 using namespace wb2;
 extern "C" {
-int wb2_ens_metrics(wb2_ctx*, const void*, const void*, int, int32_t, int64_t, int64_t,
-                    const int64_t*, const int64_t*, const wb2_weights*, int, double*) {
-  set_error("wb2_ens_metrics: not implemented in this build");
-  return WB2_EUNSUPPORTED;
-}
 int wb2_regrid_conservative(wb2_ctx*, const float*, float*, int64_t, int64_t, int64_t,
                             const wb2_csr*, const wb2_csr*) {
   set_error("wb2_regrid_conservative: not implemented in this build");

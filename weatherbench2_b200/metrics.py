@@ -500,3 +500,11 @@ class ACC(Metric):
         return cov / np.sqrt(ff * tt)
 
     return _finish(_dataset_from(res, acc), native)
+
+
+# Ensemble metrics live in _ensemble.py (they need the helpers above).
+from weatherbench2_b200._ensemble import (  # noqa: E402  pylint: disable=wrong-import-position
+    CRPS, CRPSSkill, CRPSSpread, DebiasedEnsembleMeanMSE, EnergyScore,
+    EnergyScoreSkill, EnergyScoreSpread, EnsembleMeanMSE,
+    EnsembleMeanRMSESqrtBeforeTimeAvg, EnsembleMetric,
+    EnsembleStddevSqrtBeforeTimeAvg, EnsembleVariance, _get_n_ensemble)
