@@ -1,0 +1,306 @@
+// K4 -- zonal energy spectrum (sm_100a).
+//
+// Replaces ZonalEnergySpectrum.compute (weatherbench2/derived_variables.py:
+// 592-626):  F = rfft(x, axis=lon, norm='forward');  S_k = |F_k|^2 * (1 if k == 0
+// else 2) (the Nyquist bin is doubled too, :600);  S *= circumference(lat) (:626).
+// Optionally sums over time on the device, which is what the driver script does
+// right after (xbeam.Mean(['time']), scripts/compute_zonal_energy_spectrum.py:234).
+//
+// Algorithm: a real FFT of length N = 2 * N2 per latitude row as one complex
+// FFT of length N2 (z_j = x_2j + i x_2j+1, i.e. the row read as float2) plus the
+// standard split post-pass.  The complex FFT is a Stockham autosort FFT in
+// shared memory with mixed radices {4, 2, 5, 3} (N2 = 720 = 4*4*5*3*3 for 1440
+// longitudes); the first stage reads straight from HBM (coalesced float2), the
+// post-pass multiplies |X_k|^2 by c_k * scale[row] / N^2 and either writes or
+// accumulates in registers over the time loop (deterministic: a CTA owns its
+// output rows and walks time in order).  Twiddles come from double-precision
+// host tables rounded to float32 and staged in shared memory.
+//
+// Roofline: HBM, 4 B read per cell (+ 2 B written when per-time spectra are
+// kept).  Shared-memory traffic is ~10x the HBM traffic with radix <= 5
+// stages, so this first version is shared-memory-bandwidth bound.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace wb2 {
+
+constexpr int kSpThreads = 256;
+constexpr int kSpMaxStages = 16;
+constexpr int kSpMaxAcc = 24;
+
+struct SpecParams {
+  const float* x;
+  float* out;
+  const float2* tw2;   // W_N2^k, k = 0..N2-1
+  const float2* twn;   // W_N^k,  k = 0..N2
+  const float* scale;  // [nrow]  circumference / N^2
+  int64_t nfield_out;
+  int32_t ntimes;
+  int32_t nrow, n, n2, nk;
+  int32_t rows_per_block, nblk;
+  int32_t nstage;
+  int32_t radix[kSpMaxStages];
+  int32_t accumulate;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i:  (x, y) -> (y, -x)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+template <int R> __device__ __forceinline__ void dft(float2 (&v)[R]);
+
+template <> __device__ __forceinline__ void dft<1>(float2 (&)[1]) {}
+template <> __device__ __forceinline__ void dft<2>(float2 (&v)[2]) {
+  const float2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <> __device__ __forceinline__ void dft<3>(float2 (&v)[3]) {
+  const float s = 0.86602540378443864676f;
+  const float2 a = v[0], t1 = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+  const float2 m = make_float2(a.x - 0.5f * t1.x, a.y - 0.5f * t1.y);
+  const float2 n = make_float2(s * d.y, -s * d.x);  // -i * s * d
+  v[0] = cadd(a, t1);
+  v[1] = cadd(m, n);
+  v[2] = csub(m, n);
+}
+template <> __device__ __forceinline__ void dft<4>(float2 (&v)[4]) {
+  const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+  const float2 t2 = cadd(v[1], v[3]), t3 = mul_mi(csub(v[1], v[3]));
+  v[0] = cadd(t0, t2);
+  v[2] = csub(t0, t2);
+  v[1] = cadd(t1, t3);
+  v[3] = csub(t1, t3);
+}
+template <> __device__ __forceinline__ void dft<5>(float2 (&v)[5]) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+  const float2 a = v[0];
+  const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+  const float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+  const float2 m1 = make_float2(a.x + c1 * t1.x + c2 * t2.x, a.y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(a.x + c2 * t1.x + c1 * t2.x, a.y + c2 * t1.y + c1 * t2.y);
+  const float2 n1 = mul_mi(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+  const float2 n2 = mul_mi(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+  v[0] = cadd(a, cadd(t1, t2));
+  v[1] = cadd(m1, n1);
+  v[4] = csub(m1, n1);
+  v[2] = cadd(m2, n2);
+  v[3] = csub(m2, n2);
+}
+
+// One Stockham stage of radix R over `nrows` rows held in `src` (or read from
+// global memory when FROM_GLOBAL), writing `dst`.
+template <int R, bool FROM_GLOBAL>
+__device__ __forceinline__ void stage(const float2* __restrict__ src, float2* __restrict__ dst,
+                                      const float2* __restrict__ gsrc, int64_t grow_stride,
+                                      const float2* __restrict__ tw2, int n2, int ns, int nrows) {
+  const int t = n2 / R;
+  const int step = n2 / (ns * R);
+  const int total = nrows * t;
+  for (int idx = threadIdx.x; idx < total; idx += kSpThreads) {
+    const int row = idx / t;
+    const int j = idx - row * t;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (FROM_GLOBAL) v[r] = __ldcs(gsrc + row * grow_stride + j + r * t);
+      else v[r] = src[row * n2 + j + r * t];
+    }
+    const int k = j % ns;
+    if (ns > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r * k * step]);  // r*k*step < n2
+    }
+    dft<R>(v);
+    const int j0 = (j / ns) * ns * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[row * n2 + j0 + r * ns] = v[r];
+  }
+}
+
+__global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf_a = reinterpret_cast<float2*>(smem_raw);
+  float2* buf_b = buf_a + size_t(p.rows_per_block) * p.n2;
+  float2* tw2 = buf_b + size_t(p.rows_per_block) * p.n2;
+  float2* twn = tw2 + p.n2;
+
+  for (int i = threadIdx.x; i < p.n2; i += kSpThreads) tw2[i] = p.tw2[i];
+  for (int i = threadIdx.x; i <= p.n2; i += kSpThreads) twn[i] = p.twn[i];
+  __syncthreads();
+
+  const int64_t slot = blockIdx.x / p.nblk;
+  const int blk = blockIdx.x % p.nblk;
+  const int row0 = blk * p.rows_per_block;
+  const int nrows = min(p.rows_per_block, p.nrow - row0);
+  const int total_out = nrows * p.nk;
+
+  float acc[kSpMaxAcc];
+#pragma unroll
+  for (int i = 0; i < kSpMaxAcc; ++i) acc[i] = 0.f;
+
+  for (int ti = 0; ti < p.ntimes; ++ti) {
+    const int64_t field = int64_t(ti) * p.nfield_out + slot;
+    const float2* g =
+        reinterpret_cast<const float2*>(p.x + (field * p.nrow + row0) * int64_t(p.n));
+    float2* src = buf_b;
+    float2* dst = buf_a;
+    int ns = 1;
+    for (int s = 0; s < p.nstage; ++s) {
+      const int r = p.radix[s];
+      if (s == 0) {
+        switch (r) {
+          case 1: stage<1, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          case 2: stage<2, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          case 3: stage<3, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          case 4: stage<4, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          default: stage<5, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+        }
+      } else {
+        switch (r) {
+          case 2: stage<2, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          case 3: stage<3, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          case 4: stage<4, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+          default: stage<5, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
+        }
+      }
+      __syncthreads();
+      float2* tmp = src;
+      src = dst;
+      dst = tmp;
+      ns *= r;
+    }
+    // `src` now holds Z = DFT_N2(z).  Split into the real-input spectrum:
+    //   X_k = (Z_k + conj Z_{N2-k}) / 2 - (i/2) W_N^k (Z_k - conj Z_{N2-k})
+#pragma unroll
+    for (int it = 0; it < kSpMaxAcc; ++it) {
+      const int idx = threadIdx.x + it * kSpThreads;
+      if (idx < total_out) {
+        const int row = idx / p.nk;
+        const int k = idx - row * p.nk;
+        const float2 zk = src[row * p.n2 + (k == p.n2 ? 0 : k)];
+        float2 zc = src[row * p.n2 + (k == 0 ? 0 : p.n2 - k)];
+        zc.y = -zc.y;
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+        const float2 d = csub(zk, zc);
+        const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+        const float2 xk = cadd(e, cmul(twn[k], o));
+        const float pw = (xk.x * xk.x + xk.y * xk.y) * (k == 0 ? 1.f : 2.f) * p.scale[row0 + row];
+        acc[it] += pw;
+      }
+    }
+    __syncthreads();  // buffers are reused by the next time step
+  }
+
+#pragma unroll
+  for (int it = 0; it < kSpMaxAcc; ++it) {
+    const int idx = threadIdx.x + it * kSpThreads;
+    if (idx < total_out) {
+      float* o = p.out + (slot * p.nrow + row0) * int64_t(p.nk) + idx;
+      *o = p.accumulate ? *o + acc[it] : acc[it];
+    }
+  }
+}
+
+static bool factorize(int n2, int* radix, int* nstage) {
+  int n = n2, ns = 0;
+  const int order[4] = {4, 2, 5, 3};
+  for (int oi = 0; oi < 4; ++oi) {
+    const int r = order[oi];
+    while (n % r == 0) {
+      if (ns >= kSpMaxStages) return false;
+      radix[ns++] = r;
+      n /= r;
+    }
+  }
+  if (n != 1) return false;
+  if (ns == 0) radix[ns++] = 1;
+  *nstage = ns;
+  return true;
+}
+
+}  // namespace wb2
+
+using namespace wb2;
+
+extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
+                                  int32_t ncol, const double* scale, float* out,
+                                  int32_t accumulate, int64_t nfield_out) {
+  WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
+  WB2_REQUIRE(nrow > 0 && ncol > 1, "bad grid %d x %d", nrow, ncol);
+  WB2_REQUIRE(nfield >= 0, "nfield < 0");
+  if (nfield == 0) return WB2_OK;
+  WB2_REQUIRE(x && out && scale, "NULL argument");
+  if (!accumulate) nfield_out = nfield;
+  WB2_REQUIRE(nfield_out > 0 && nfield % nfield_out == 0,
+              "nfield (%lld) must be a multiple of nfield_out (%lld)",
+              static_cast<long long>(nfield), static_cast<long long>(nfield_out));
+  if (ncol % 2 != 0) {
+    set_error("wb2_zonal_spectrum: odd number of longitudes (%d) is not supported", ncol);
+    return WB2_EUNSUPPORTED;
+  }
+  SpecParams p;
+  p.n = ncol; p.n2 = ncol / 2; p.nk = p.n2 + 1; p.nrow = nrow;
+  if (p.n2 == 1) {
+    p.nstage = 1;
+    p.radix[0] = 1;
+  } else if (!factorize(p.n2, p.radix, &p.nstage)) {
+    set_error("wb2_zonal_spectrum: %d longitudes: N/2 must factor into 2, 3 and 5", ncol);
+    return WB2_EUNSUPPORTED;
+  }
+  DeviceGuard guard(ctx->device);
+
+  // host tables in double precision, rounded once to float32
+  std::vector<float2> tw2(p.n2), twn(p.n2 + 1);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < p.n2; ++k) {
+    const double a = -two_pi * k / p.n2;
+    tw2[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+  }
+  for (int k = 0; k <= p.n2; ++k) {
+    const double a = -two_pi * k / p.n;
+    twn[k] = make_float2(static_cast<float>(cos(a)), static_cast<float>(sin(a)));
+  }
+  std::vector<float> sc(nrow);
+  for (int i = 0; i < nrow; ++i)
+    sc[i] = static_cast<float>(scale[i] / (double(ncol) * double(ncol)));
+
+  // rows per CTA: ~40 KB per ping-pong buffer, bounded by the register
+  // accumulators (kSpMaxAcc outputs per thread)
+  int rpb = static_cast<int>((40 * 1024) / (size_t(p.n2) * sizeof(float2)));
+  if (rpb < 1) rpb = 1;
+  if (rpb > 32) rpb = 32;
+  while (rpb > 1 && rpb * p.nk > kSpMaxAcc * kSpThreads) --rpb;
+  WB2_REQUIRE(rpb * p.nk <= kSpMaxAcc * kSpThreads,
+              "wb2_zonal_spectrum: %d longitudes exceed the supported row length", ncol);
+  if (rpb > nrow) rpb = nrow;
+  p.rows_per_block = rpb;
+  p.nblk = (nrow + rpb - 1) / rpb;
+  p.nfield_out = nfield_out;
+  p.ntimes = static_cast<int>(nfield / nfield_out);
+  p.accumulate = accumulate ? 1 : 0;
+  const size_t smem = (size_t(2) * rpb * p.n2 + p.n2 + p.n2 + 1) * sizeof(float2);
+  WB2_REQUIRE(smem <= 220 * 1024, "wb2_zonal_spectrum: row too long for shared memory");
+
+  Packer pk(ctx);
+  size_t o1 = pk.add(tw2.data(), tw2.size() * sizeof(float2));
+  size_t o2 = pk.add(twn.data(), twn.size() * sizeof(float2));
+  size_t o3 = pk.add(sc.data(), sc.size() * sizeof(float));
+  WB2_TRY(pk.commit());
+  p.x = x; p.out = out;
+  p.tw2 = pk.dev<float2>(o1); p.twn = pk.dev<float2>(o2); p.scale = pk.dev<float>(o3);
+  if (smem > 48 * 1024)
+    WB2_CUDA_TRY(cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  spectrum_kernel<<<static_cast<unsigned>(nfield_out * p.nblk), kSpThreads, smem, ctx->stream>>>(p);
+  WB2_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  WB2_TRY(pk.release());
+  return WB2_OK;
+}

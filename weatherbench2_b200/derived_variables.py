@@ -1,0 +1,153 @@
+"""Derived variables on the hot path: `ZonalEnergySpectrum` with the API of
+weatherbench2/derived_variables.py:29-56, 531-626.  The rFFT, the power
+spectrum and the circumference scaling run in csrc/spectrum.cu.
+(The other derived variables of the reference -- wind speed, vorticity, ... --
+are cheap stencils outside the scope of SURVEY.md section 8.)
+"""
+from __future__ import annotations
+
+import dataclasses
+import typing as t
+
+import numpy as np
+
+from weatherbench2_b200 import _lib
+from weatherbench2_b200 import xarray_lite as xl
+
+EARTH_RADIUS_M = 1000 * (6357 + 6378) / 2  # weatherbench2/schema.py:59
+
+
+@dataclasses.dataclass
+class DerivedVariable:
+  """Derived variable base class (derived_variables.py:28-56)."""
+
+  @property
+  def base_variables(self) -> list[str]:
+    return []
+
+  @property
+  def core_dims(self):
+    raise NotImplementedError
+
+  @property
+  def all_input_core_dims(self) -> set[str]:
+    return set().union(*self.core_dims[0])
+
+  def compute(self, dataset):
+    raise NotImplementedError
+
+
+@dataclasses.dataclass
+class ZonalEnergySpectrum(DerivedVariable):
+  """Energy spectrum along the zonal direction
+  (derived_variables.py:531-626).
+
+  S[0] = C |F[0]|^2, S[k] = 2 C |F[k]|^2 for k > 0 (the Nyquist bin included),
+  F = rfft(f, norm='forward'), C = circumference of the latitude circle.
+  Output dims: the input dims with `longitude` replaced by a trailing
+  `zonal_wavenumber`; coords `frequency` (1 / m) and `wavelength` (m) with dims
+  (zonal_wavenumber, latitude).
+  """
+
+  variable_name: str
+
+  @property
+  def base_variables(self) -> list[str]:
+    return [self.variable_name]
+
+  @property
+  def core_dims(self):
+    return (['longitude'],), ['zonal_wavenumber']
+
+  def _circumference(self, latitude: np.ndarray) -> np.ndarray:
+    """derived_variables.py:578-581."""
+    circum_at_equator = 2 * np.pi * EARTH_RADIUS_M
+    return np.cos(np.asarray(latitude) * np.pi / 180) * circum_at_equator
+
+  def lon_spacing_m(self, dataset) -> xl.DataArray:
+    """Spacing (meters) between longitudes (derived_variables.py:583-590)."""
+    ds = xl.from_xarray(dataset)
+    lon = ds['longitude'].values
+    lat = ds['latitude'].values
+    diffs = np.diff(lon)
+    if np.max(np.abs(diffs - diffs[0])) > 1e-3:
+      raise ValueError(f'Expected uniform longitude spacing. {lon=}')
+    return xl.DataArray(self._circumference(lat) * diffs[0] / 360,
+                        ('latitude',), {'latitude': lat})
+
+  def compute(self, dataset, time_sum_dim: t.Optional[str] = None):
+    """Zonal power at wavenumber and frequency (derived_variables.py:592-626).
+
+    time_sum_dim (extension): when given, the spectrum is additionally summed
+    over that dimension on the device (the script's `xbeam.Mean(['time'])`,
+    scripts/compute_zonal_energy_spectrum.py:234, is sum / count); the
+    dimension is dropped from the result.
+    """
+    native = xl.is_native_xarray(dataset)
+    ds = xl.from_xarray(dataset)
+    spacing = self.lon_spacing_m(ds).values
+    da = ds[self.variable_name]
+    lat = ds['latitude'].values
+    lon = ds['longitude'].values
+    if 'latitude' not in da.dims or 'longitude' not in da.dims:
+      raise ValueError(f'{self.variable_name} needs latitude and longitude')
+    outer = tuple(d for d in da.dims if d not in ('latitude', 'longitude'))
+    if time_sum_dim is not None:
+      if time_sum_dim not in outer:
+        raise ValueError(f'{time_sum_dim!r} is not a dimension of the data')
+      outer = (time_sum_dim,) + tuple(d for d in outer if d != time_sum_dim)
+    work = da.transpose(*(outer + ('latitude', 'longitude')))
+    data = work.data
+    ctx = _lib.default_context()
+    nlat, nlon = lat.size, lon.size
+    nk = nlon // 2 + 1
+    oshape = tuple(work.sizes[d] for d in outer)
+    nfield = int(np.prod(oshape)) if oshape else 1
+    scale = self._circumference(lat)
+    nt = oshape[0] if time_sum_dim is not None else 1
+    nout = nfield // nt
+    res_shape = (oshape[1:] if time_sum_dim is not None else oshape) + (nlat,
+                                                                        nk)
+    is_torch = xl._is_torch(data)  # pylint: disable=protected-access
+    if is_torch and data.is_cuda:
+      import torch  # pylint: disable=import-outside-toplevel
+      x = data.to(torch.float32).contiguous()
+      out = torch.zeros(res_shape, device=data.device, dtype=torch.float32)
+      torch.cuda.current_stream(data.device).synchronize()
+      ctx.zonal_spectrum(x.data_ptr(), nfield, nlat, nlon, scale,
+                         out.data_ptr(), time_sum_dim is not None, nout)
+      ctx.synchronize()
+      values = out
+    else:
+      x = np.ascontiguousarray(np.asarray(data), dtype=np.float32)
+      src = ctx.to_device(x)
+      dst = ctx.malloc(max(1, nout * nlat * nk * 4))
+      try:
+        ctx.lib.wb2_memset(ctx.handle, dst, 0, nout * nlat * nk * 4)
+        ctx.zonal_spectrum(src, nfield, nlat, nlon, scale, dst,
+                           time_sum_dim is not None, nout)
+        values = ctx.from_device(dst, res_shape, np.float32)
+      finally:
+        ctx.free(src)
+        ctx.free(dst)
+    out_outer = outer[1:] if time_sum_dim is not None else outer
+    dims = out_outer + ('latitude', 'zonal_wavenumber')
+    base_frequency = np.fft.rfftfreq(nlon)  # derived_variables.py:614
+    with np.errstate(divide='ignore'):
+      frequency = base_frequency[:, None] / spacing[None, :]
+      wavelength = 1 / frequency
+    coords = {k: c for k, c in work.coords.items()
+              if 'longitude' not in c.dims and all(d in dims for d in c.dims)}
+    coords['zonal_wavenumber'] = xl.Coord(('zonal_wavenumber',), np.arange(nk))
+    coords['frequency'] = xl.Coord(('zonal_wavenumber', 'latitude'), frequency,
+                                   {'units': '1 / m'})
+    coords['wavelength'] = xl.Coord(('zonal_wavenumber', 'latitude'),
+                                    wavelength, {'units': 'm'})
+    # the reference keeps the non-core dims in place and appends the new core
+    # dim (apply_ufunc): (..., latitude, ..., zonal_wavenumber)
+    ref_dims = tuple(d for d in da.dims if d != 'longitude' and
+                     d != time_sum_dim) + ('zonal_wavenumber',)
+    result = xl.DataArray(values, dims, coords, self.variable_name)
+    if not is_torch:
+      result = result.transpose(*ref_dims)
+    return xl.to_xarray(result) if native else result
