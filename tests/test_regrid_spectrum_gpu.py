@@ -213,7 +213,13 @@ def test_spectrum_parseval_and_time_sum():
   spec = dv.compute(ds)
   spacing = dv.lon_spacing_m(ds).values
   energy = (spacing[None, None, :, None] * x.astype(np.float64) ** 2).sum(-1)
-  np.testing.assert_allclose(spec.values.sum(-1), energy, rtol=2e-3)
+  # White noise has Nyquist content, which the reference counts twice
+  # (derived_variables.py:600): sum_k S_k = (C/L) sum f^2 + C |F_{L/2}|^2.
+  nyq = np.abs(np.fft.rfft(x.astype(np.float64), axis=-1,
+                           norm='forward')[..., -1]) ** 2
+  circ = dv._circumference(lat)[None, None, :]
+  np.testing.assert_allclose(spec.values.sum(-1), energy + circ * nyq,
+                             rtol=1e-5)
   summed = dv.compute(ds, time_sum_dim='time')
   assert summed.dims == ('level', 'latitude', 'zonal_wavenumber')
   np.testing.assert_allclose(summed.values, spec.values.sum(axis=0),
