@@ -9,16 +9,21 @@
 // Algorithm: a real FFT of length N = 2 * N2 per latitude row as one complex
 // FFT of length N2 (z_j = x_2j + i x_2j+1, i.e. the row read as float2) plus the
 // standard split post-pass.  The complex FFT is a Stockham autosort FFT in
-// shared memory with mixed radices {4, 2, 5, 3} (N2 = 720 = 4*4*5*3*3 for 1440
-// longitudes); the first stage reads straight from HBM (coalesced float2), the
+// shared memory with register butterflies of radix 16, 9, 8, 5, 4, 3, 2
+// (N2 = 720 = 16 * 9 * 5 for 1440 longitudes: three passes); radix 16 / 9 / 8
+// are Cooley-Tukey composites of the 4 / 3 / 2 butterflies with compile-time
+// twiddles.  The first stage reads straight from HBM (coalesced float2); the
 // post-pass multiplies |X_k|^2 by c_k * scale[row] / N^2 and either writes or
 // accumulates in registers over the time loop (deterministic: a CTA owns its
-// output rows and walks time in order).  Twiddles come from double-precision
-// host tables rounded to float32 and staged in shared memory.
+// output rows and walks time in order).  Stage twiddles come from a
+// double-precision host table rounded to float32, staged in shared memory.
+// Shared arrays are padded by one float2 every 16 so that the stride-R writes
+// of the first stage are 2-way instead of 16-way bank conflicts; (row, j)
+// decoding uses multiply-high division.
 //
 // Roofline: HBM, 4 B read per cell (+ 2 B written when per-time spectra are
-// kept).  Shared-memory traffic is ~10x the HBM traffic with radix <= 5
-// stages, so this first version is shared-memory-bandwidth bound.
+// kept); at N = 1440 the FFT's ~30 flop-instructions per cell are close to the
+// FP32 ridge of the chip.
 #include <cmath>
 
 #include "common.cuh"
@@ -42,6 +47,7 @@ struct SpecParams {
   int32_t nstage;
   int32_t radix[kSpMaxStages];
   int32_t accumulate;
+  int32_t row_pitch;  // padded float2 per row in shared memory
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -51,6 +57,15 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 // multiply by -i:  (x, y) -> (y, -x)
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+// padded shared-memory index
+__device__ __forceinline__ int pad(int i) { return i + (i >> 4); }
+// floor(x / d) for 0 <= x < 2^20 via multiply-high; m = ceil(2^32 / d)
+__device__ __forceinline__ int fast_div(int x, unsigned m, int d) {
+  return d == 1 ? x : static_cast<int>(__umulhi(static_cast<unsigned>(x), m));
+}
+static unsigned magic(int d) {
+  return d <= 1 ? 0u : static_cast<unsigned>(((1ull << 32) + d - 1) / d);
+}
 
 template <int R> __device__ __forceinline__ void dft(float2 (&v)[R]);
 
@@ -94,41 +109,136 @@ template <> __device__ __forceinline__ void dft<5>(float2 (&v)[5]) {
   v[3] = csub(m2, n2);
 }
 
+// cos / sin of 2 pi m / N for the composite radices (compile-time indices)
+template <int N> struct Wc;
+template <> struct Wc<16> {
+  static __device__ __forceinline__ float2 w(int m) {
+    constexpr float c[16] = {1.f, 0.92387953251128674f, 0.70710678118654752f,
+                             0.38268343236508977f, 0.f, -0.38268343236508977f,
+                             -0.70710678118654752f, -0.92387953251128674f, -1.f,
+                             -0.92387953251128674f, -0.70710678118654752f,
+                             -0.38268343236508977f, 0.f, 0.38268343236508977f,
+                             0.70710678118654752f, 0.92387953251128674f};
+    constexpr float s[16] = {0.f, 0.38268343236508977f, 0.70710678118654752f,
+                             0.92387953251128674f, 1.f, 0.92387953251128674f,
+                             0.70710678118654752f, 0.38268343236508977f, 0.f,
+                             -0.38268343236508977f, -0.70710678118654752f,
+                             -0.92387953251128674f, -1.f, -0.92387953251128674f,
+                             -0.70710678118654752f, -0.38268343236508977f};
+    return make_float2(c[m], -s[m]);  // forward transform: exp(-2 pi i m / N)
+  }
+};
+template <> struct Wc<9> {
+  static __device__ __forceinline__ float2 w(int m) {
+    constexpr float c[9] = {1.f, 0.76604444311897804f, 0.17364817766693035f, -0.5f,
+                            -0.93969262078590838f, -0.93969262078590838f, -0.5f,
+                            0.17364817766693035f, 0.76604444311897804f};
+    constexpr float s[9] = {0.f, 0.64278760968653933f, 0.98480775301220806f,
+                            0.86602540378443865f, 0.34202014332566873f,
+                            -0.34202014332566873f, -0.86602540378443865f,
+                            -0.98480775301220806f, -0.64278760968653933f};
+    return make_float2(c[m], -s[m]);
+  }
+};
+template <> struct Wc<8> {
+  static __device__ __forceinline__ float2 w(int m) {
+    constexpr float c[8] = {1.f, 0.70710678118654752f, 0.f, -0.70710678118654752f, -1.f,
+                            -0.70710678118654752f, 0.f, 0.70710678118654752f};
+    constexpr float s[8] = {0.f, 0.70710678118654752f, 1.f, 0.70710678118654752f, 0.f,
+                            -0.70710678118654752f, -1.f, -0.70710678118654752f};
+    return make_float2(c[m], -s[m]);
+  }
+};
+
+// Cooley-Tukey composite of size R1 * R2 in registers:
+//   input  n = R2 * n1 + n2,  output k = k1 + R1 * k2
+template <int R1, int R2>
+__device__ __forceinline__ void dft_composite(float2 (&v)[R1 * R2]) {
+  constexpr int N = R1 * R2;
+  float2 y[R2][R1];
+#pragma unroll
+  for (int n2 = 0; n2 < R2; ++n2) {
+    float2 col[R1];
+#pragma unroll
+    for (int n1 = 0; n1 < R1; ++n1) col[n1] = v[R2 * n1 + n2];
+    dft<R1>(col);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      const int m = (n2 * k1) % N;
+      y[n2][k1] = m == 0 ? col[k1] : cmul(col[k1], Wc<N>::w(m));
+    }
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) {
+    float2 row[R2];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) row[n2] = y[n2][k1];
+    dft<R2>(row);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = row[k2];
+  }
+}
+template <> __device__ __forceinline__ void dft<16>(float2 (&v)[16]) { dft_composite<4, 4>(v); }
+template <> __device__ __forceinline__ void dft<9>(float2 (&v)[9]) { dft_composite<3, 3>(v); }
+template <> __device__ __forceinline__ void dft<8>(float2 (&v)[8]) { dft_composite<4, 2>(v); }
+
+struct StageInfo {
+  int t, ns, step;
+  unsigned m_t, m_ns;
+};
+
 // One Stockham stage of radix R over `nrows` rows held in `src` (or read from
-// global memory when FROM_GLOBAL), writing `dst`.
+// global memory when FROM_GLOBAL), writing `dst` (both padded, pitch `pitch`).
 template <int R, bool FROM_GLOBAL>
 __device__ __forceinline__ void stage(const float2* __restrict__ src, float2* __restrict__ dst,
-                                      const float2* __restrict__ gsrc, int64_t grow_stride,
-                                      const float2* __restrict__ tw2, int n2, int ns, int nrows) {
-  const int t = n2 / R;
-  const int step = n2 / (ns * R);
-  const int total = nrows * t;
+                                      const float2* __restrict__ gsrc, int n2, int pitch,
+                                      const float2* __restrict__ tw2, const StageInfo si,
+                                      int nrows) {
+  const int total = nrows * si.t;
   for (int idx = threadIdx.x; idx < total; idx += kSpThreads) {
-    const int row = idx / t;
-    const int j = idx - row * t;
+    const int row = fast_div(idx, si.m_t, si.t);
+    const int j = idx - row * si.t;
     float2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (FROM_GLOBAL) v[r] = __ldcs(gsrc + row * grow_stride + j + r * t);
-      else v[r] = src[row * n2 + j + r * t];
+      if (FROM_GLOBAL) v[r] = __ldcs(gsrc + row * n2 + j + r * si.t);
+      else v[r] = src[row * pitch + pad(j + r * si.t)];
     }
-    const int k = j % ns;
-    if (ns > 1) {
+    const int q = fast_div(j, si.m_ns, si.ns);
+    const int k = j - q * si.ns;
+    if (si.ns > 1) {
+      const int base = k * si.step;  // r * k * step < n2
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r * k * step]);  // r*k*step < n2
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r * base]);
     }
     dft<R>(v);
-    const int j0 = (j / ns) * ns * R + k;
+    const int j0 = q * si.ns * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[row * n2 + j0 + r * ns] = v[r];
+    for (int r = 0; r < R; ++r) dst[row * pitch + pad(j0 + r * si.ns)] = v[r];
+  }
+}
+
+template <bool FROM_GLOBAL>
+__device__ __forceinline__ void run_stage(int r, const float2* src, float2* dst, const float2* g,
+                                          int n2, int pitch, const float2* tw2,
+                                          const StageInfo si, int nrows) {
+  switch (r) {
+    case 1: stage<1, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 2: stage<2, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 3: stage<3, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 4: stage<4, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 5: stage<5, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 8: stage<8, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    case 9: stage<9, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
+    default: stage<16, FROM_GLOBAL>(src, dst, g, n2, pitch, tw2, si, nrows); break;
   }
 }
 
 __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf_a = reinterpret_cast<float2*>(smem_raw);
-  float2* buf_b = buf_a + size_t(p.rows_per_block) * p.n2;
-  float2* tw2 = buf_b + size_t(p.rows_per_block) * p.n2;
+  float2* buf_b = buf_a + size_t(p.rows_per_block) * p.row_pitch;
+  float2* tw2 = buf_b + size_t(p.rows_per_block) * p.row_pitch;
   float2* twn = tw2 + p.n2;
 
   for (int i = threadIdx.x; i < p.n2; i += kSpThreads) tw2[i] = p.tw2[i];
@@ -140,6 +250,7 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p
   const int row0 = blk * p.rows_per_block;
   const int nrows = min(p.rows_per_block, p.nrow - row0);
   const int total_out = nrows * p.nk;
+  const unsigned m_nk = (unsigned)(((1ull << 32) + p.nk - 1) / p.nk);
 
   float acc[kSpMaxAcc];
 #pragma unroll
@@ -154,22 +265,14 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p
     int ns = 1;
     for (int s = 0; s < p.nstage; ++s) {
       const int r = p.radix[s];
-      if (s == 0) {
-        switch (r) {
-          case 1: stage<1, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          case 2: stage<2, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          case 3: stage<3, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          case 4: stage<4, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          default: stage<5, true>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-        }
-      } else {
-        switch (r) {
-          case 2: stage<2, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          case 3: stage<3, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          case 4: stage<4, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-          default: stage<5, false>(src, dst, g, p.n2, tw2, p.n2, ns, nrows); break;
-        }
-      }
+      StageInfo si;
+      si.t = p.n2 / r;
+      si.ns = ns;
+      si.step = p.n2 / (ns * r);
+      si.m_t = (unsigned)(((1ull << 32) + si.t - 1) / si.t);
+      si.m_ns = (unsigned)(((1ull << 32) + ns - 1) / ns);
+      if (s == 0) run_stage<true>(r, src, dst, g, p.n2, p.row_pitch, tw2, si, nrows);
+      else run_stage<false>(r, src, dst, g, p.n2, p.row_pitch, tw2, si, nrows);
       __syncthreads();
       float2* tmp = src;
       src = dst;
@@ -182,10 +285,10 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p
     for (int it = 0; it < kSpMaxAcc; ++it) {
       const int idx = threadIdx.x + it * kSpThreads;
       if (idx < total_out) {
-        const int row = idx / p.nk;
+        const int row = static_cast<int>(__umulhi(static_cast<unsigned>(idx), m_nk));
         const int k = idx - row * p.nk;
-        const float2 zk = src[row * p.n2 + (k == p.n2 ? 0 : k)];
-        float2 zc = src[row * p.n2 + (k == 0 ? 0 : p.n2 - k)];
+        const float2 zk = src[row * p.row_pitch + pad(k == p.n2 ? 0 : k)];
+        float2 zc = src[row * p.row_pitch + pad(k == 0 ? 0 : p.n2 - k)];
         zc.y = -zc.y;
         const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
         const float2 d = csub(zk, zc);
@@ -210,8 +313,8 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p
 
 static bool factorize(int n2, int* radix, int* nstage) {
   int n = n2, ns = 0;
-  const int order[4] = {4, 2, 5, 3};
-  for (int oi = 0; oi < 4; ++oi) {
+  const int order[7] = {16, 9, 8, 5, 4, 3, 2};
+  for (int oi = 0; oi < 7; ++oi) {
     const int r = order[oi];
     while (n % r == 0) {
       if (ns >= kSpMaxStages) return false;
@@ -271,13 +374,14 @@ extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, 
   for (int i = 0; i < nrow; ++i)
     sc[i] = static_cast<float>(scale[i] / (double(ncol) * double(ncol)));
 
-  // rows per CTA: ~40 KB per ping-pong buffer, bounded by the register
-  // accumulators (kSpMaxAcc outputs per thread)
-  int rpb = static_cast<int>((40 * 1024) / (size_t(p.n2) * sizeof(float2)));
+  // rows per CTA: ~46 KB per ping-pong buffer, bounded by the register
+  // accumulators (kSpMaxAcc outputs per thread) and by fast_div's range
+  p.row_pitch = p.n2 + (p.n2 >> 4) + 1;
+  int rpb = static_cast<int>((46 * 1024) / (size_t(p.row_pitch) * sizeof(float2)));
   if (rpb < 1) rpb = 1;
   if (rpb > 32) rpb = 32;
   while (rpb > 1 && rpb * p.nk > kSpMaxAcc * kSpThreads) --rpb;
-  WB2_REQUIRE(rpb * p.nk <= kSpMaxAcc * kSpThreads,
+  WB2_REQUIRE(rpb * p.nk <= kSpMaxAcc * kSpThreads && rpb * p.nk < (1 << 20),
               "wb2_zonal_spectrum: %d longitudes exceed the supported row length", ncol);
   if (rpb > nrow) rpb = nrow;
   p.rows_per_block = rpb;
@@ -285,8 +389,9 @@ extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, 
   p.nfield_out = nfield_out;
   p.ntimes = static_cast<int>(nfield / nfield_out);
   p.accumulate = accumulate ? 1 : 0;
-  const size_t smem = (size_t(2) * rpb * p.n2 + p.n2 + p.n2 + 1) * sizeof(float2);
+  const size_t smem = (size_t(2) * rpb * p.row_pitch + p.n2 + p.n2 + 1) * sizeof(float2);
   WB2_REQUIRE(smem <= 220 * 1024, "wb2_zonal_spectrum: row too long for shared memory");
+  (void)magic;
 
   Packer pk(ctx);
   size_t o1 = pk.add(tw2.data(), tw2.size() * sizeof(float2));
