@@ -327,7 +327,10 @@ def main():
       'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                    'unit': 'GB/s', 'frac': achieved / peak,
                    'traffic': args.traffic, 'peak_source': peak_src,
-                   'kernel': 'det_metrics_kernel<float,4,CLIM> (+ finalize)',
+                   'kernel': ('det_metrics_kernel<float,4,CLIM> (LDG path)'
+                              if os.environ.get('WB2_DET_PATH') == 'ldg' else
+                              'det_tma_kernel<CLIM,!SKIPNA> (TMA ring)') +
+                             ' + finalize',
                    'kernel_ms': kernel_ms,
                    'algorithmic_bytes_per_launch':
                        cells_per_step * BYTES_PER_CELL},

@@ -176,6 +176,27 @@ def test_spectrum_matches_oracle(nlon):
   assert got.coords['frequency'].attrs['units'] == '1 / m'
 
 
+@pytest.mark.parametrize('nlon', [64, 240, 360, 512, 720, 1440])
+def test_spectrum_fixed_plan_vs_generic_kernel(monkeypatch, nlon):
+  """Sizes with a compile-time radix plan (spectrum_fixed_kernel) against the
+  generic runtime-plan kernel and the oracle; 23 latitude rows so that the
+  last CTA owns a ragged row block."""
+  from weatherbench2_b200 import derived_variables as dvs, xarray_lite as xl
+  x, dims, lat, lon = _spectrum_case(nlon, nlat=23, outer=(2, 2), seed=nlon)
+  ds = xl.Dataset({'u': (dims, x)},
+                  {'time': np.arange(2), 'level': np.arange(2),
+                   'latitude': lat, 'longitude': lon})
+  want, _, _, _ = orc.zonal_energy_spectrum(x, dims, lat, lon)
+  res = {}
+  for path in ('fixed', 'generic'):
+    monkeypatch.setenv('WB2_SPECTRUM_PATH', path)
+    res[path] = dvs.ZonalEnergySpectrum('u').compute(ds).values.astype(
+        np.float64)
+    _check_spectrum(res[path], want)
+  power = want.sum(axis=-1, keepdims=True)
+  assert np.max(np.abs(res['fixed'] - res['generic']) / power) < 2e-6
+
+
 def test_spectrum_longitude_first_layout_and_peak():
   """Mock layout (..., longitude, latitude) and the spectral-peak test of
   derived_variables_test.py:290-321."""

@@ -311,6 +311,152 @@ __global__ void __launch_bounds__(kSpThreads) spectrum_kernel(const SpecParams p
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fixed-plan variant: N2 and the (up to three) radices are template constants,
+// so every division, stride, twiddle step and padded index folds at compile
+// time, and the post-pass handles the bins k and N2 - k together (they share
+// both loads and the complex product W_N^k * O):
+//     X_k = E + W O,   X_{N2-k} = conj(E - W O).
+// ---------------------------------------------------------------------------
+template <int R, int NS, int N2, bool FROM_GLOBAL>
+__device__ __forceinline__ void stage_ct(const float2* __restrict__ src, float2* __restrict__ dst,
+                                         const float2* __restrict__ gsrc,
+                                         const float2* __restrict__ tw2, int nrows) {
+  constexpr int T = N2 / R;
+  constexpr int STEP = N2 / (NS * R);
+  constexpr int PITCH = N2 + (N2 >> 4) + 1;
+  const int total = nrows * T;
+  for (int idx = threadIdx.x; idx < total; idx += kSpThreads) {
+    const int row = idx / T;
+    const int j = idx - row * T;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (FROM_GLOBAL) v[r] = __ldcs(gsrc + row * N2 + j + r * T);
+      else v[r] = src[row * PITCH + pad(j + r * T)];
+    }
+    const int q = j / NS;
+    const int k = j - q * NS;
+    if (NS > 1) {
+      const int base = k * STEP;
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r * base]);
+    }
+    dft<R>(v);
+    const int j0 = q * (NS * R) + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) dst[row * PITCH + pad(j0 + r * NS)] = v[r];
+  }
+}
+
+template <int N2, int R0, int R1, int R2>
+__global__ void __launch_bounds__(kSpThreads) spectrum_fixed_kernel(const SpecParams p) {
+  static_assert(R0 * R1 * R2 == N2, "radix plan must multiply to N2");
+  constexpr int PITCH = N2 + (N2 >> 4) + 1;
+  constexpr int NK = N2 + 1;
+  constexpr int NPAIR = N2 / 2 + 1;  // pair p handles bins p and N2 - p
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf_a = reinterpret_cast<float2*>(smem_raw);
+  float2* buf_b = buf_a + size_t(p.rows_per_block) * PITCH;
+  float2* tw2 = buf_b + size_t(p.rows_per_block) * PITCH;
+  float2* twn = tw2 + N2;
+
+  for (int i = threadIdx.x; i < N2; i += kSpThreads) tw2[i] = p.tw2[i];
+  for (int i = threadIdx.x; i <= N2; i += kSpThreads) twn[i] = p.twn[i];
+  __syncthreads();
+
+  const int64_t slot = blockIdx.x / p.nblk;
+  const int blk = blockIdx.x % p.nblk;
+  const int row0 = blk * p.rows_per_block;
+  const int nrows = min(p.rows_per_block, p.nrow - row0);
+  const int total_pairs = nrows * NPAIR;
+
+  constexpr int kPairIters = kSpMaxAcc / 2;
+  float acc_lo[kPairIters], acc_hi[kPairIters];
+#pragma unroll
+  for (int i = 0; i < kPairIters; ++i) { acc_lo[i] = 0.f; acc_hi[i] = 0.f; }
+
+  for (int ti = 0; ti < p.ntimes; ++ti) {
+    const int64_t field = int64_t(ti) * p.nfield_out + slot;
+    const float2* g =
+        reinterpret_cast<const float2*>(p.x + (field * p.nrow + row0) * int64_t(2 * N2));
+    stage_ct<R0, 1, N2, true>(nullptr, buf_a, g, tw2, nrows);
+    __syncthreads();
+    const float2* z = buf_a;
+    if (R1 > 1) {
+      stage_ct<R1, R0, N2, false>(buf_a, buf_b, g, tw2, nrows);
+      __syncthreads();
+      z = buf_b;
+      if (R2 > 1) {
+        stage_ct<R2, R0 * R1, N2, false>(buf_b, buf_a, g, tw2, nrows);
+        __syncthreads();
+        z = buf_a;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kPairIters; ++it) {
+      const int idx = threadIdx.x + it * kSpThreads;
+      if (idx < total_pairs) {
+        const int row = idx / NPAIR;
+        const int k = idx - row * NPAIR;
+        const float2 zk = z[row * PITCH + pad(k)];
+        float2 zc = z[row * PITCH + pad(k == 0 ? 0 : N2 - k)];
+        zc.y = -zc.y;
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+        const float2 d = csub(zk, zc);
+        const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+        const float2 wo = cmul(twn[k], o);
+        const float2 xa = cadd(e, wo), xb = csub(e, wo);
+        const float sc = p.scale[row0 + row];
+        acc_lo[it] += (xa.x * xa.x + xa.y * xa.y) * (k == 0 ? 1.f : 2.f) * sc;
+        acc_hi[it] += (xb.x * xb.x + xb.y * xb.y) * 2.f * sc;
+      }
+    }
+    __syncthreads();  // buffers are reused by the next time step
+  }
+
+#pragma unroll
+  for (int it = 0; it < kPairIters; ++it) {
+    const int idx = threadIdx.x + it * kSpThreads;
+    if (idx < total_pairs) {
+      const int row = idx / NPAIR;
+      const int k = idx - row * NPAIR;
+      float* o = p.out + ((slot * p.nrow + row0 + row) * int64_t(NK));
+      o[k] = p.accumulate ? o[k] + acc_lo[it] : acc_lo[it];
+      if (2 * k != N2) o[N2 - k] = p.accumulate ? o[N2 - k] + acc_hi[it] : acc_hi[it];
+    }
+  }
+}
+
+template <int N2, int R0, int R1, int R2>
+static int launch_fixed(wb2_ctx* ctx, const SpecParams& p, size_t smem, unsigned grid) {
+  auto kernel = spectrum_fixed_kernel<N2, R0, R1, R2>;
+  if (smem > 48 * 1024)
+    WB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  kernel<<<grid, kSpThreads, smem, ctx->stream>>>(p);
+  WB2_CUDA_TRY(cudaGetLastError());
+  return WB2_OK;
+}
+
+// Returns 1 if a fixed-plan kernel exists for n2 (and was launched), else 0.
+static int try_fixed(wb2_ctx* ctx, const SpecParams& p, size_t smem, unsigned grid) {
+  const char* force = getenv("WB2_SPECTRUM_PATH");
+  if (force && strcmp(force, "generic") == 0) return 0;
+  if (p.rows_per_block * (p.n2 / 2 + 1) > (kSpMaxAcc / 2) * kSpThreads) return 0;
+  int rc;
+  switch (p.n2) {
+    case 720: rc = launch_fixed<720, 16, 9, 5>(ctx, p, smem, grid); break;  // 1440 (0.25 deg)
+    case 360: rc = launch_fixed<360, 9, 8, 5>(ctx, p, smem, grid); break;   // 720  (0.5 deg)
+    case 180: rc = launch_fixed<180, 9, 5, 4>(ctx, p, smem, grid); break;   // 360  (1 deg)
+    case 120: rc = launch_fixed<120, 8, 5, 3>(ctx, p, smem, grid); break;   // 240  (1.5 deg)
+    case 256: rc = launch_fixed<256, 16, 16, 1>(ctx, p, smem, grid); break; // 512
+    case 32: rc = launch_fixed<32, 16, 2, 1>(ctx, p, smem, grid); break;    // 64   (5.625 deg)
+    default: return 0;
+  }
+  return rc == WB2_OK ? 1 : rc;
+}
+
 static bool factorize(int n2, int* radix, int* nstage) {
   int n = n2, ns = 0;
   const int order[7] = {16, 9, 8, 5, 4, 3, 2};
@@ -400,11 +546,17 @@ extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, 
   WB2_TRY(pk.commit());
   p.x = x; p.out = out;
   p.tw2 = pk.dev<float2>(o1); p.twn = pk.dev<float2>(o2); p.scale = pk.dev<float>(o3);
-  if (smem > 48 * 1024)
-    WB2_CUDA_TRY(cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
-  spectrum_kernel<<<static_cast<unsigned>(nfield_out * p.nblk), kSpThreads, smem, ctx->stream>>>(p);
-  WB2_CUDA_TRY(cudaGetLastError());
+  const unsigned grid = static_cast<unsigned>(nfield_out * p.nblk);
+  const int frc = try_fixed(ctx, p, smem, grid);
+  if (frc < 0) return frc;
+  if (frc == 0) {
+    if (smem > 48 * 1024)
+      WB2_CUDA_TRY(cudaFuncSetAttribute(spectrum_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    spectrum_kernel<<<grid, kSpThreads, smem, ctx->stream>>>(p);
+    WB2_CUDA_TRY(cudaGetLastError());
+  }
   ctx->launches += 1;
   WB2_TRY(pk.release());
   return WB2_OK;
