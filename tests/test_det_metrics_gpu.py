@@ -198,6 +198,77 @@ def test_tma_and_ldg_paths_agree(ctx, monkeypatch, skipna, clim):
       assert (s[:, 3:6] == 0).all() and (s[:, 7:] == 0).all()
 
 
+@pytest.mark.parametrize('skipna', [False, True])
+@pytest.mark.parametrize('clim', [False, True])
+def test_segmented_tma_path_many_regions(ctx, monkeypatch, skipna, clim):
+  """Longitude boxes cut the row into many column segments: the
+  lane-contiguous TMA kernel (det_tma_seg.cu) against the LDG kernel and the
+  oracle.  20 regions exercise the split into launches of <= 16 (8 with
+  skipna) regions; NaN/Inf sit in cells some regions mask out."""
+  from weatherbench2_b200 import _lib, _spatial as sp, regions as R
+  rs = np.random.RandomState(33)
+  nlat, nlon, nb = 91, 360, 6
+  lat, lon = _grid(nlat, nlon)
+  dims = ('b', 'latitude', 'longitude')
+  f = rs.standard_normal((nb, nlat, nlon)).astype(np.float32)
+  t = rs.standard_normal((nb, nlat, nlon)).astype(np.float32)
+  c = rs.standard_normal((nb, nlat, nlon)).astype(np.float32)
+  f[:, 80:, 200:230] = np.nan     # only inside some boxes
+  t[:, :5, 10:20] = np.inf
+  if skipna:
+    f[rs.rand(*f.shape) < 0.003] = np.nan
+  boxes = [(None, None, None, None), (-20, 20, None, None), (20, 90, 0, 180),
+           (35, 75, 347.5, 42.5), (25, 60, 240, 290), (25, 60, 145, 180),
+           (-45, -12.5, 120, 175), (-37.5, -22.5, 15, 50),
+           (-52.5, -20, 287.5, 327.5), (-90, -60, None, None)]
+  boxes = boxes + [(-30 + i, 40 - i, 13.0 * i, 13.0 * i + 77) for i in
+                   range(10)]
+  preg, oreg = [], []
+  for la0, la1, lo0, lo1 in boxes:
+    lat_s = slice(la0, la1)
+    if lo0 is not None and lo1 is not None and lo0 > lo1:
+      lon_p = [slice(lo0, None), slice(0, lo1)]
+    else:
+      lon_p = slice(lo0, lo1)
+    preg.append(R.SliceRegion(lat_slice=lat_s, lon_slice=lon_p))
+    oreg.append(orc.SliceRegion(lat_slice=lat_s, lon_slice=lon_p))
+  preg.append(R.ExtraTropicalRegion())
+  oreg.append(orc.ExtraTropicalRegion())
+  nreg = len(preg)
+  df, dt_, dc = ctx.to_device(f), ctx.to_device(t), ctx.to_device(c)
+  base = min(df, dt_, dc)
+  slab = nlat * nlon
+  offs = [np.arange(nb, dtype=np.int64) * slab + (p - base) // 4
+          for p in (df, dt_, dc)]
+  (_, spec), = sp.build_weights(ctx, lat, lon, preg, 'lat_lon', nlon)
+  assert spec.nseg > 8 and spec.nregion == nreg == 21
+  out = ctx.malloc(nb * nreg * _lib.DET_NSTAT * 8)
+  res = {}
+  for path in ('tma', 'ldg'):
+    monkeypatch.setenv('WB2_DET_PATH', path)
+    ctx.det_metrics(base, base, base if clim else None, _lib.F32, offs[0],
+                    offs[1], offs[2] if clim else None, spec, skipna, out)
+    res[path] = ctx.from_device(out, (nb, nreg, _lib.DET_NSTAT), np.float64)
+  for p in (df, dt_, dc, out):
+    ctx.free(p)
+  np.testing.assert_array_equal(np.isnan(res['tma']), np.isnan(res['ldg']))
+  np.testing.assert_allclose(res['tma'], res['ldg'], rtol=3e-6, atol=2e-4)
+  for ri, region in enumerate(oreg):
+    s = res['tma'][:, ri]
+    kw = dict(lat=lat, lon=lon, region=region, skipna=skipna)
+    want, _ = orc.mse(f, dims, t, dims, **kw)
+    with np.errstate(invalid='ignore', divide='ignore'):
+      np.testing.assert_allclose(s[:, 0] / s[:, 6], want, rtol=3e-6)
+      want, _ = orc.bias(f, dims, t, dims, **kw)
+      np.testing.assert_allclose(s[:, 2] / s[:, 6], want, rtol=1e-4,
+                                 atol=3e-6)
+      if clim:
+        want, _ = orc.acc(f, dims, t, dims, c, dims, **kw)
+        acc = (s[:, 3] / s[:, 7]) / np.sqrt((s[:, 4] / s[:, 8]) *
+                                            (s[:, 5] / s[:, 9]))
+        np.testing.assert_allclose(acc, want, rtol=1e-4, atol=3e-6)
+
+
 def test_unaligned_offsets_take_scalar_path(ctx):
   """Slabs that start at odd element offsets (no 16-byte alignment)."""
   from weatherbench2_b200 import _lib, _spatial as sp

@@ -352,6 +352,10 @@ int det_metrics_tma(wb2_ctx* ctx, bool clim, const void* f, const void* t, const
                     const int64_t* d_off_c, const double* d_row_w, const double* d_seg_w,
                     const wb2_weights* w, int skipna, double* out);
 
+int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, const void* c,
+                        int64_t nfield, const int64_t* d_off_f, const int64_t* d_off_t,
+                        const int64_t* d_off_c, const wb2_weights* w, int skipna, double* out);
+
 static bool all_multiple(const int64_t* v, int64_t n, int64_t m) {
   if (!v) return true;
   for (int64_t i = 0; i < n; ++i)
@@ -439,6 +443,17 @@ int det_metrics_impl(wb2_ctx* ctx, int mode, const void* f, const void* t, const
         w->ncol % 4 == 0 && mode != MODE_VECTOR) {
       int trc = det_metrics_tma(ctx, mode == MODE_CLIM, f, t, c, nfield, p.off_f, p.off_t,
                                 p.off_c, p.row_w, p.seg_w, w, skipna, out);
+      if (trc < 0) return trc;
+      if (trc == 1) {
+        WB2_TRY(pk.release());
+        return WB2_OK;
+      }
+    }
+    // many regions: column segments -> lane-contiguous TMA kernel
+    if (want_tma && dtype == WB2_F32 && vec_ok && !weighted && w->nseg > 1 &&
+        w->ncol % 4 == 0 && mode != MODE_VECTOR) {
+      int trc = det_metrics_tma_seg(ctx, mode == MODE_CLIM, f, t, c, nfield, p.off_f, p.off_t,
+                                    p.off_c, w, skipna, out);
       if (trc < 0) return trc;
       if (trc == 1) {
         WB2_TRY(pk.release());

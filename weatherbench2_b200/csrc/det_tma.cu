@@ -24,6 +24,7 @@
 // (offsets, row stride and ncol multiples of 4 elements), one column segment,
 // no per-column / per-cell weight factor.  Everything else takes the LDG kernel.
 #include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace wb2 {
 
@@ -51,43 +52,6 @@ struct TmaParams {
   int32_t stage_op_bytes;   // bytes reserved per operand per stage (128-B mult.)
   int32_t maxslots;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-      ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 
 template <bool CLIM, bool SKIPNA>
 __device__ __forceinline__ void tma_cell(float f, float t, float c, float* acc) {
@@ -142,7 +106,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 2);  // both warps of the consuming pair
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   __syncthreads();
 
@@ -298,6 +262,17 @@ __global__ void det_tma_finalize_kernel(const double* __restrict__ partial,
     }
     out[field * per_field + i] = v;
   }
+}
+
+// Host wrapper so that other translation units (det_tma_seg.cu) can run the
+// fixed-order finalize without relocatable device code.
+int launch_det_tma_finalize(wb2_ctx* ctx, const double* partial, double* out, int64_t nfield,
+                            int64_t ntiles, int ncta, int tiles_per_field, int maxslots,
+                            int per_field) {
+  det_tma_finalize_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
+      partial, out, ntiles, ncta, tiles_per_field, maxslots, per_field);
+  WB2_CUDA_TRY(cudaGetLastError());
+  return WB2_OK;
 }
 
 // Returns 1 if the TMA path ran, 0 if the launch is not eligible, < 0 on error.

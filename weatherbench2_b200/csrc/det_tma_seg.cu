@@ -1,0 +1,403 @@
+// K1 fast path for MANY REGIONS -- TMA-staged persistent kernel with
+// lane-contiguous column spans (sm_100a).
+//
+// The official WB2 evaluation runs 13-16 regions (scripts/evaluate.py:345-395);
+// their longitude boxes cut a row into ~15 column segments.  Reducing every
+// (row, segment) across the warp (det_metrics.cu / det_tma.cu) then costs more
+// than the arithmetic.  Here the tile already sits in shared memory (same TMA
+// ring as det_tma.cu), so a lane can own a CONTIGUOUS span of columns: it walks
+// its span once, keeps unweighted f32 partial sums, and whenever the span
+// crosses a segment boundary (or ends) it adds  W_r(row, seg) * partial  into
+// per-region REGISTER accumulators for all regions of the launch -- about two
+// FMAs per cell instead of a 5-step butterfly per statistic per segment.
+// Every 8 tiles (and at field changes) the register accumulators are
+// warp-reduced into float64 shared-memory accumulators; fields are flushed to
+// per-(CTA, warp, field) float64 partials which det_tma_finalize_kernel adds in
+// a fixed order.  Span width is odd so the scalar LDS of a warp are
+// conflict-free.
+//
+// Eligibility: float32, 16-byte aligned slabs, no per-column / per-cell weight
+// factor, nregion <= RCH (16; 8 with skipna) -- the host splits longer region
+// lists into several launches.
+#include <algorithm>
+
+#include "common.cuh"
+#include "tma_utils.cuh"
+
+namespace wb2 {
+
+constexpr int kSegConsumerWarps = 8;
+constexpr int kSegThreads = (kSegConsumerWarps + 1) * 32;
+constexpr int kSegTilesInFlight = kSegConsumerWarps / 2;
+constexpr int kSegDump = 8;  // tiles between register -> shared float64 dumps
+
+struct TmaSegParams {
+  const float* f;
+  const float* t;
+  const float* c;
+  const int64_t* off_f;
+  const int64_t* off_t;
+  const int64_t* off_c;
+  const float* row_wf;       // [R][nrow] float32 copy of row_w
+  const float* seg_wf;       // [nseg][RCH] float32, zero padded
+  const int32_t* seg_start;  // [nseg + 1]
+  double* partial;           // [ncta][warps][maxslots][R][WB2_DET_NSTAT]
+  int64_t ntiles;
+  int32_t nrow, ncol;
+  int64_t row_stride;
+  int32_t nregion, nseg;
+  int32_t zero_skip;
+  int32_t nstage;
+  int32_t stage_op_bytes;
+  int32_t maxslots;
+};
+
+template <bool CLIM, bool SKIPNA>
+__device__ __forceinline__ void seg_cell(float f, float t, float c, float* part) {
+  constexpr int NSUM = CLIM ? 6 : 3;
+  const float d = f - t;
+  if (SKIPNA) {
+    if (d == d) {
+      part[0] += d * d;
+      part[1] += fabsf(d);
+      part[2] += d;
+      part[NSUM] += 1.0f;
+    }
+  } else {
+    part[0] += d * d;
+    part[1] += fabsf(d);
+    part[2] += d;
+  }
+  if (CLIM) {
+    const float fa = f - c, ta = t - c;
+    const float v3 = fa * ta, v4 = fa * fa, v5 = ta * ta;
+    if (SKIPNA) {
+      if (v3 == v3) { part[3] += v3; part[NSUM + 1] += 1.0f; }
+      if (fa == fa) { part[4] += v4; part[NSUM + 2] += 1.0f; }
+      if (ta == ta) { part[5] += v5; part[NSUM + 3] += 1.0f; }
+    } else {
+      part[3] += v3;
+      part[4] += v4;
+      part[5] += v5;
+    }
+  }
+}
+
+template <bool CLIM, bool SKIPNA, int RCH>
+__global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSegParams p) {
+  constexpr int NOPER = CLIM ? 3 : 2;
+  constexpr int NSUM = CLIM ? 6 : 3;
+  // per-piece values: sums, then counts (skipna) or one cell count (!skipna)
+  constexpr int NCNT = SKIPNA ? (CLIM ? 4 : 1) : 1;
+  constexpr int NS = NSUM + NCNT;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nstage = p.nstage;
+  const size_t stage_bytes = size_t(NOPER) * p.stage_op_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stage_bytes * nstage);
+  uint64_t* empty = full + nstage;
+  double* dacc = reinterpret_cast<double*>(empty + nstage);  // [warps][RCH][NS]
+  float* s_segw = reinterpret_cast<float*>(dacc + kSegConsumerWarps * RCH * NS);  // [nseg][RCH]
+  int* s_segstart = reinterpret_cast<int*>(s_segw + size_t(p.nseg) * RCH);       // [nseg + 1]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < p.nseg * RCH; i += kSegThreads) s_segw[i] = p.seg_wf[i];
+  for (int i = threadIdx.x; i <= p.nseg; i += kSegThreads) s_segstart[i] = p.seg_start[i];
+  for (int i = threadIdx.x; i < kSegConsumerWarps * RCH * NS; i += kSegThreads) dacc[i] = 0.0;
+  __syncthreads();
+
+  const int64_t per = p.ntiles / gridDim.x, extra = p.ntiles % gridDim.x;
+  const int64_t b = blockIdx.x;
+  const int64_t t0 = b * per + (b < extra ? b : extra);
+  const int64_t t1 = t0 + per + (b < extra ? 1 : 0);
+  const int64_t ncta_tiles = t1 - t0;
+  const int64_t first_field = t0 / p.nrow;
+
+  if (warp == kSegConsumerWarps) {
+    // ------------------------------ producer --------------------------------
+    if (lane == 0) {
+      int64_t field = first_field;
+      int row = static_cast<int>(t0 - first_field * p.nrow);
+      const float* pf = p.f + p.off_f[field];
+      const float* pt = p.t + p.off_t[field];
+      const float* pc = CLIM ? p.c + p.off_c[field] : nullptr;
+      const uint32_t bytes = static_cast<uint32_t>(p.ncol) * 4u;
+      int s = 0;
+      uint32_t use = 0;
+      for (int64_t j = 0; j < ncta_tiles; ++j) {
+        if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+        const int64_t e = int64_t(row) * p.row_stride;
+        unsigned char* dst = smem + stage_bytes * s;
+        mbar_arrive_expect_tx(&full[s], bytes * NOPER);
+        tma_load_1d(dst, pf + e, bytes, &full[s]);
+        tma_load_1d(dst + p.stage_op_bytes, pt + e, bytes, &full[s]);
+        if (CLIM) tma_load_1d(dst + 2 * p.stage_op_bytes, pc + e, bytes, &full[s]);
+        if (++s == nstage) { s = 0; ++use; }
+        if (++row == p.nrow) {
+          row = 0;
+          ++field;
+          if (j + 1 < ncta_tiles) {
+            pf = p.f + p.off_f[field];
+            pt = p.t + p.off_t[field];
+            if (CLIM) pc = p.c + p.off_c[field];
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------- consumers --------------------------------
+  const int R = p.nregion;
+  const bool zero_skip = p.zero_skip != 0;
+  const int pair = warp >> 1, half = warp & 1;
+  const int half_cols = (p.ncol + 1) >> 1;
+  const int h0 = half ? half_cols : 0;
+  const int h1 = half ? p.ncol : half_cols;
+  const int span = (((h1 - h0) + 31) >> 5) | 1;  // odd -> conflict-free scalar LDS
+  const int c0 = min(h1, h0 + lane * span);
+  const int c1 = min(h1, c0 + span);
+  int k0 = 0;  // segment of the first column of this lane's span (fixed)
+  while (k0 + 1 < p.nseg && s_segstart[k0 + 1] <= c0) ++k0;
+
+  float accr[RCH][NS];
+#pragma unroll
+  for (int r = 0; r < RCH; ++r)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) accr[r][i] = 0.f;
+  double* my_dacc = dacc + warp * RCH * NS;
+  int since_dump = 0;
+  int64_t cur_field = -1;
+
+  auto dump = [&]() {
+    // register accumulators -> float64 shared accumulators of this warp
+#pragma unroll
+    for (int r = 0; r < RCH; ++r) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        const float v = warp_sum(accr[r][i]);
+        if (lane == 0) my_dacc[r * NS + i] += double(v);
+        accr[r][i] = 0.f;
+      }
+    }
+    since_dump = 0;
+    __syncwarp();
+  };
+  auto flush_field = [&](int64_t field) {
+    if (field < 0) return;
+    dump();
+    const int slot = static_cast<int>(field - first_field);
+    double* out = p.partial +
+                  ((int64_t(blockIdx.x) * kSegConsumerWarps + warp) * p.maxslots + slot) *
+                      int64_t(R) * WB2_DET_NSTAT;
+    for (int idx = lane; idx < R * WB2_DET_NSTAT; idx += 32) {
+      const int r = idx / WB2_DET_NSTAT;
+      const int st = idx - r * WB2_DET_NSTAT;
+      int slot_i = -1;
+      if (st < 6) {
+        if (st < NSUM) slot_i = st;
+      } else {
+        const int j = st - 6;
+        if (SKIPNA) { if (j < NCNT) slot_i = NSUM + j; }
+        else if (CLIM || j == 0) slot_i = NSUM;
+      }
+      out[idx] = slot_i >= 0 ? my_dacc[r * NS + slot_i] : 0.0;
+    }
+    __syncwarp();
+    for (int i = lane; i < RCH * NS; i += 32) my_dacc[i] = 0.0;
+    __syncwarp();
+  };
+
+  int64_t field = first_field;
+  int row = static_cast<int>(t0 - first_field * p.nrow) + pair;
+  int s = pair;
+  uint32_t use = 0;
+  for (int64_t j = pair; j < ncta_tiles; j += kSegTilesInFlight) {
+    while (row >= p.nrow) { row -= p.nrow; ++field; }
+    if (field != cur_field) {
+      flush_field(cur_field);
+      cur_field = field;
+    }
+    // float32 row weights of all regions for this row (broadcast loads, issued
+    // before the wait)
+    float u[RCH];
+#pragma unroll
+    for (int r = 0; r < RCH; ++r) u[r] = r < R ? __ldg(p.row_wf + int64_t(r) * p.nrow + row) : 0.f;
+
+    const unsigned char* src = smem + stage_bytes * s;
+    const float* sf = reinterpret_cast<const float*>(src);
+    const float* st_ = reinterpret_cast<const float*>(src + p.stage_op_bytes);
+    const float* sc = reinterpret_cast<const float*>(src + 2 * p.stage_op_bytes);
+
+    float part[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) part[i] = 0.f;
+    int k = k0;
+    int next_b = s_segstart[k + 1];
+
+    auto apply = [&](int kk) {
+      const float* wv = s_segw + kk * RCH;
+#pragma unroll
+      for (int r = 0; r < RCH; ++r) {
+        const float w = u[r] * wv[r];
+        if (w != 0.f || !zero_skip) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) accr[r][i] = fmaf(w, part[i], accr[r][i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) part[i] = 0.f;
+    };
+
+    mbar_wait(&full[s], use & 1);
+    for (int col = c0; col < c1; ++col) {
+      if (col == next_b) {
+        apply(k);
+        ++k;
+        next_b = s_segstart[k + 1];
+      }
+      seg_cell<CLIM, SKIPNA>(sf[col], st_[col], CLIM ? sc[col] : 0.f, part);
+      if (!SKIPNA) part[NSUM] += 1.0f;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (c1 > c0) apply(k);
+
+    if (++since_dump >= kSegDump) dump();
+    row += kSegTilesInFlight;
+    s += kSegTilesInFlight;
+    if (s >= nstage) { s -= nstage; ++use; }
+  }
+  flush_field(cur_field);
+}
+
+int launch_det_tma_finalize(wb2_ctx* ctx, const double* partial, double* out, int64_t nfield,
+                            int64_t ntiles, int ncta, int tiles_per_field, int maxslots,
+                            int per_field);
+
+// Returns 1 if the kernel ran, 0 if not eligible, < 0 on error.  Handles the
+// regions [r0, r0 + nreg) of `w`; `out` is the full [nfield][w->nregion][10]
+// array (this launch fills only its regions).
+template <int RCH>
+static int launch_seg(wb2_ctx* ctx, bool clim, bool skipna, const TmaSegParams& p, int ncta,
+                      size_t smem) {
+  auto go = [&](auto kernel) -> int {
+    WB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    kernel<<<ncta, kSegThreads, smem, ctx->stream>>>(p);
+    WB2_CUDA_TRY(cudaGetLastError());
+    return WB2_OK;
+  };
+  if (clim) return skipna ? go(det_tma_seg_kernel<true, true, RCH>)
+                          : go(det_tma_seg_kernel<true, false, RCH>);
+  return skipna ? go(det_tma_seg_kernel<false, true, RCH>)
+                : go(det_tma_seg_kernel<false, false, RCH>);
+}
+
+__global__ void seg_scatter_kernel(const double* __restrict__ tmp, double* __restrict__ out,
+                                   int nreg, int r0, int rtotal) {
+  // tmp [nfield][nreg][10] -> out [nfield][rtotal][10] at region offset r0
+  const int64_t field = blockIdx.x;
+  for (int i = threadIdx.x; i < nreg * WB2_DET_NSTAT; i += blockDim.x)
+    out[(field * rtotal + r0) * WB2_DET_NSTAT + i] = tmp[field * nreg * WB2_DET_NSTAT + i];
+}
+
+int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, const void* c,
+                        int64_t nfield, const int64_t* d_off_f, const int64_t* d_off_t,
+                        const int64_t* d_off_c, const wb2_weights* w, int skipna, double* out) {
+  const int noper = clim ? 3 : 2;
+  if (w->ncol * 4 < 512 || w->ncol % 4 != 0) return 0;
+  const int rch = skipna ? 8 : 16;
+  const int nsum = clim ? 6 : 3;
+  const int ns = nsum + (skipna ? (clim ? 4 : 1) : 1);
+  const int stage_op_bytes = (w->ncol * 4 + 127) / 128 * 128;
+  const size_t fixed = size_t(kSegConsumerWarps) * rch * ns * sizeof(double) +
+                       size_t(w->nseg) * rch * sizeof(float) + size_t(w->nseg + 1) * sizeof(int) +
+                       256;
+  const size_t budget = 220 * 1024;
+  if (fixed >= budget) return 0;
+  int nstage = static_cast<int>((budget - fixed) / (size_t(noper) * stage_op_bytes + 16));
+  nstage = nstage / kSegTilesInFlight * kSegTilesInFlight;
+  if (nstage > 32) nstage = 32;
+  if (nstage < 2 * kSegTilesInFlight) return 0;
+  const size_t smem = size_t(nstage) * noper * stage_op_bytes + 2 * nstage * sizeof(uint64_t) + fixed;
+
+  const int64_t ntiles = nfield * w->nrow;
+  int ncta = ctx->num_sms;
+  if (ntiles < ncta) ncta = static_cast<int>(ntiles);
+  const int64_t per = (ntiles + ncta - 1) / ncta;
+  const int maxslots = static_cast<int>((per + w->nrow - 1) / w->nrow) + 1;
+
+  for (int r0 = 0; r0 < w->nregion; r0 += rch) {
+    const int nreg = std::min(rch, w->nregion - r0);
+    // float32 weights of this region chunk
+    std::vector<float> row_wf(size_t(nreg) * w->nrow), seg_wf(size_t(w->nseg) * rch, 0.f);
+    for (int r = 0; r < nreg; ++r) {
+      for (int i = 0; i < w->nrow; ++i)
+        row_wf[size_t(r) * w->nrow + i] = static_cast<float>(w->row_w[size_t(r0 + r) * w->nrow + i]);
+      for (int k = 0; k < w->nseg; ++k)
+        seg_wf[size_t(k) * rch + r] = static_cast<float>(w->seg_w[size_t(r0 + r) * w->nseg + k]);
+    }
+    const size_t per_field = size_t(nreg) * WB2_DET_NSTAT;
+    const size_t part_bytes =
+        size_t(ncta) * kSegConsumerWarps * maxslots * per_field * sizeof(double);
+    const size_t tmp_bytes = size_t(nfield) * per_field * sizeof(double);
+    const size_t need = part_bytes + tmp_bytes;
+    if (need > ctx->tma_partial_cap) {
+      if (ctx->tma_partial) {
+        WB2_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        WB2_CUDA_TRY(cudaFree(ctx->tma_partial));
+        ctx->tma_partial = nullptr;
+        ctx->tma_partial_cap = 0;
+      }
+      WB2_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->tma_partial), need));
+      ctx->tma_partial_cap = need;
+    }
+    Packer pk(ctx);
+    size_t o1 = pk.add(row_wf.data(), row_wf.size() * sizeof(float));
+    size_t o2 = pk.add(seg_wf.data(), seg_wf.size() * sizeof(float));
+    size_t o3 = pk.add(w->seg_start, size_t(w->nseg + 1) * sizeof(int32_t));
+    WB2_TRY(pk.commit());
+
+    TmaSegParams p;
+    p.f = static_cast<const float*>(f);
+    p.t = static_cast<const float*>(t);
+    p.c = static_cast<const float*>(c);
+    p.off_f = d_off_f; p.off_t = d_off_t; p.off_c = d_off_c;
+    p.row_wf = pk.dev<float>(o1); p.seg_wf = pk.dev<float>(o2);
+    p.seg_start = pk.dev<int32_t>(o3);
+    p.partial = ctx->tma_partial;
+    p.ntiles = ntiles;
+    p.nrow = w->nrow; p.ncol = w->ncol; p.row_stride = w->row_stride;
+    p.nregion = nreg; p.nseg = w->nseg; p.zero_skip = w->zero_skip;
+    p.nstage = nstage; p.stage_op_bytes = stage_op_bytes; p.maxslots = maxslots;
+    WB2_CUDA_TRY(cudaMemsetAsync(p.partial, 0, part_bytes, ctx->stream));
+    int rc = skipna ? launch_seg<8>(ctx, clim, true, p, ncta, smem)
+                    : launch_seg<16>(ctx, clim, false, p, ncta, smem);
+    if (rc != WB2_OK) return rc;
+    double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->tma_partial) + part_bytes);
+    const bool direct = (nreg == w->nregion);
+    WB2_TRY(launch_det_tma_finalize(ctx, p.partial, direct ? out : tmp, nfield, ntiles, ncta,
+                                    w->nrow, maxslots, static_cast<int>(per_field)));
+    ctx->launches += 2;
+    if (!direct) {
+      seg_scatter_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
+          tmp, out, nreg, r0, w->nregion);
+      WB2_CUDA_TRY(cudaGetLastError());
+      ctx->launches += 1;
+    }
+    WB2_TRY(pk.release());
+  }
+  return 1;
+}
+
+}  // namespace wb2

@@ -87,23 +87,15 @@ __global__ void __launch_bounds__(kRgThreads) regrid_kernel(const RegridParams p
     }
     const float4 w4 = *reinterpret_cast<const float4*>(wtab + bi * kRgGroup);
     const float w[kRgGroup] = {w4.x, w4.y, w4.z, w4.w};
-    float x0[kRgDpt], one[kRgDpt];
 #pragma unroll
     for (int i = 0; i < kRgDpt; ++i) {
       const bool ok = xv[i] == xv[i];
-      x0[i] = ok ? xv[i] : 0.f;
-      one[i] = ok ? 1.f : 0.f;
-    }
-    // a source row feeds one or two of the G targets: the weights come from a
-    // shared-memory broadcast, so this branch is warp-uniform
+      const float x0 = ok ? xv[i] : 0.f;
+      const float one = ok ? 1.f : 0.f;
 #pragma unroll
-    for (int a = 0; a < kRgGroup; ++a) {
-      if (w[a] != 0.f) {
-#pragma unroll
-        for (int i = 0; i < kRgDpt; ++i) {
-          y[i][a] = fmaf(w[a], x0[i], y[i][a]);
-          v[i][a] = fmaf(w[a], one[i], v[i][a]);
-        }
+      for (int a = 0; a < kRgGroup; ++a) {
+        y[i][a] = fmaf(w[a], x0, y[i][a]);
+        v[i][a] = fmaf(w[a], one, v[i][a]);
       }
     }
   }

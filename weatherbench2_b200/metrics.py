@@ -449,31 +449,35 @@ class Bias(Metric):
         res, lambda st: _ratio(st[..., 2], st[..., 6])), native)
 
 
+def _spatial_variant_not_built(name):
+  raise NotImplementedError(
+      f'{name}: the map-output (Spatial*) metrics are elementwise kernels with '
+      'a device-side time mean; they are the next scope row (SURVEY.md section '
+      '8f) and are not built yet.  There is deliberately no NumPy fallback.')
+
+
 @dataclasses.dataclass
 class SpatialMSE(Metric):
-  """MSE without spatial averaging (metrics.py:304-316); elementwise."""
+  """MSE without spatial averaging (metrics.py:304-316) -- not built yet."""
 
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    del skipna
-    return (forecast - truth) ** 2
+    _spatial_variant_not_built('SpatialMSE')
 
 
 @dataclasses.dataclass
 class SpatialMAE(Metric):
-  """MAE without spatial averaging (metrics.py:333-345); elementwise."""
+  """MAE without spatial averaging (metrics.py:333-345) -- not built yet."""
 
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    del skipna
-    return abs(forecast - truth)
+    _spatial_variant_not_built('SpatialMAE')
 
 
 @dataclasses.dataclass
 class SpatialBias(Metric):
-  """Bias without spatial averaging (metrics.py:362-374); elementwise."""
+  """Bias without spatial averaging (metrics.py:362-374) -- not built yet."""
 
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    del skipna
-    return forecast - truth
+    _spatial_variant_not_built('SpatialBias')
 
 
 @dataclasses.dataclass
