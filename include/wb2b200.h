@@ -172,6 +172,18 @@ int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                     const int64_t* off_x, const int64_t* off_t,
                     const wb2_weights* w, int skipna, double* out);
 
+/* ---- K3: energy score -------------------------------------------------------
+ * Replaces the per-member weighted L2 norms of EnergyScoreSkill / Spread
+ * (metrics.py:1471-1517): every member is read once.
+ *   out   device [nfield][nregion][4][nmember] float64:
+ *         [0][m] sum W (x_m - t)^2         [1][m] sum W (x_m - x_{m+1})^2 (m < M-1)
+ *         [2][m], [3][m] the matching weight sums
+ * NaN propagates (skipna = False semantics); at most 4 regions per launch.     */
+int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                     int32_t nmember, int64_t member_stride, int64_t nfield,
+                     const int64_t* off_x, const int64_t* off_t,
+                     const wb2_weights* w, double* out);
+
 /* ---- K5: conservative regridding -------------------------------------------
  * Replaces ConservativeRegridder.regrid_array (= _nanmean,
  * weatherbench2/regridding.py:502-536).  The two weight matrices

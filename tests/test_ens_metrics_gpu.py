@@ -204,6 +204,40 @@ def test_energy_score(ensemble_size):
     np.testing.assert_array_equal(spread.values, 0)
 
 
+@pytest.mark.parametrize('ensemble_size', [2, 17, 50])
+def test_energy_score_k3_regions_and_skipna_fallback(ensemble_size):
+  """K3 (every member read once) with regions incl. a land mask, against the
+  oracle; skipna=True takes the K1-on-member-views path and must agree too."""
+  from weatherbench2_b200 import metrics, regions as R
+  fds, tds, forecast, truth, lat, lon = _pair(
+      ensemble_size=ensemble_size, lead_stop='1 day',
+      spatial_resolution_in_degrees=10, time_stop='2019-12-01T06')
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  rs = np.random.RandomState(2)
+  lsm = (rs.rand(lat.size, lon.size) > 0.5).astype(float)
+  pairs = [(None, None),
+           (R.SliceRegion(lat_slice=slice(-30, 50), lon_slice=slice(40, 250)),
+            orc.SliceRegion(lat_slice=slice(-30, 50),
+                            lon_slice=slice(40, 250))),
+           (R.LandRegion(lsm), orc.LandRegion(lsm))]
+  for preg, oreg in pairs:
+    a5 = (f, fd, t, tdm, 'realization', lat, lon)
+    want_sk, wd = orc.energy_score_skill(*a5, region=oreg)
+    want_sp, _ = orc.energy_score_spread(f, fd, 'realization', lat, lon,
+                                         region=oreg)
+    for skipna in (False, True):
+      sk = metrics.EnergyScoreSkill().compute_chunk(
+          fds, tds, region=preg, skipna=skipna)['geopotential']
+      sp_ = metrics.EnergyScoreSpread().compute_chunk(
+          fds, tds, region=preg, skipna=skipna)['geopotential']
+      es = metrics.EnergyScore().compute_chunk(
+          fds, tds, region=preg, skipna=skipna)['geopotential']
+      _cmp(sk, want_sk, wd, rtol=1e-5)
+      _cmp(sp_, want_sp, wd, rtol=1e-5)
+      _cmp(es, want_sk - 0.5 * want_sp, wd, rtol=1e-5, atol=1e-6)
+
+
 def test_regions_lon_lat_layout_and_device_inputs():
   """K2 with several regions (incl. a land mask) in one pass, and with the
   ensemble resident on the device."""

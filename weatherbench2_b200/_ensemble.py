@@ -226,10 +226,45 @@ class DebiasedEnsembleMeanMSE(EnsembleMetric):
 
 
 # ------------------------------------------------------------------------------
-# Energy score: per-member weighted L2 norms -> K1 (statistic 0) on member views
+# Energy score.  skipna=False: K3 (csrc/ens_energy.cu) reads every member once.
+# skipna=True: per-member weighted L2 norms via K1 on member views.
 # ------------------------------------------------------------------------------
 def _member_mean(ds: xl.Dataset, ens_dim: str, skipna: bool) -> xl.Dataset:
   return ds.mean(ens_dim, skipna=skipna)
+
+
+def _energy_k3(forecast: xl.Dataset, truth: xl.Dataset, ens_dim: str, region):
+  """(skill, spread) Datasets from ONE pass over the ensemble (K3)."""
+  ctx = m._context()  # pylint: disable=protected-access
+  names = m._common_vars(forecast, truth)  # pylint: disable=protected-access
+  lat, lon = m._lat_lon(forecast)  # pylint: disable=protected-access
+  skill, spread = xl.Dataset(), xl.Dataset()
+  for name in names:
+    f_da, t_da = forecast[name], truth[name]
+    if LAT not in f_da.dims or LON not in f_da.dims:
+      continue
+    x_op = sp.prepare_operand(f_da, None, np.float32)
+    t_op = sp.prepare_operand(t_da, x_op.layout, np.float32)
+    (st,), (dims,), (mm,) = sp.run_energy_score(
+        ctx, [x_op], [t_op], ens_dim, lat, lon, [region],
+        m._global_cell_cache)  # pylint: disable=protected-access
+    st = st[..., 0, :, :]  # single region
+    coords = m._result_coords(dims, f_da, t_da)  # pylint: disable=protected-access
+    coords.pop(ens_dim, None)
+    with np.errstate(invalid='ignore', divide='ignore'):
+      sk = np.sqrt(m._ratio(st[..., 0, :], st[..., 2, :])).mean(axis=-1)  # pylint: disable=protected-access
+      if mm > 1:
+        sd = np.sqrt(m._ratio(st[..., 1, :mm - 1],  # pylint: disable=protected-access
+                              st[..., 3, :mm - 1])).mean(axis=-1)
+      else:
+        sd = np.zeros(st.shape[:-2], dtype=np.float64)  # metrics.py:1481-1489
+    skill[name] = xl.DataArray(sk, dims, coords, name)
+    spread[name] = xl.DataArray(sd, dims, coords, name)
+  return skill, spread
+
+
+def _use_k3(forecast, ens_dim, skipna) -> bool:
+  return (not skipna) and forecast.sizes[ens_dim] <= 64
 
 
 @dataclasses.dataclass
@@ -239,6 +274,9 @@ class EnergyScoreSkill(EnsembleMetric):
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
     forecast, truth, native = m._prep(forecast, truth)  # pylint: disable=protected-access
     _get_n_ensemble(forecast, self.ensemble_dim)
+    if _use_k3(forecast, self.ensemble_dim, skipna):
+      return m._finish(_energy_k3(forecast, truth, self.ensemble_dim,  # pylint: disable=protected-access
+                                  region)[0], native)
     res = m._det_request(forecast, truth, region, skipna)  # pylint: disable=protected-access
     with np.errstate(invalid='ignore'):
       l2 = m._dataset_from(  # pylint: disable=protected-access
@@ -254,6 +292,9 @@ class EnergyScoreSpread(EnsembleMetric):
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
     forecast, truth, native = m._prep(forecast, truth)  # pylint: disable=protected-access
     n_ensemble = _get_n_ensemble(forecast, self.ensemble_dim)
+    if _use_k3(forecast, self.ensemble_dim, skipna):
+      return m._finish(_energy_k3(forecast, truth, self.ensemble_dim,  # pylint: disable=protected-access
+                                  region)[1], native)
     if n_ensemble == 1:
       res = m._det_request(forecast, m._zero_truth(forecast), region, skipna)  # pylint: disable=protected-access
       zeros = m._dataset_from(  # pylint: disable=protected-access
@@ -275,6 +316,11 @@ class EnergyScore(EnsembleMetric):
   """ES = skill - spread / 2 (metrics.py:1402-1464)."""
 
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
+    fc, tr, native = m._prep(forecast, truth)  # pylint: disable=protected-access
+    _get_n_ensemble(fc, self.ensemble_dim)
+    if _use_k3(fc, self.ensemble_dim, skipna):
+      skill, spread = _energy_k3(fc, tr, self.ensemble_dim, region)
+      return m._finish(skill - 0.5 * spread, native)  # pylint: disable=protected-access
     return EnergyScoreSkill(self.ensemble_dim).compute_chunk(
         forecast, truth, region=region, skipna=skipna
     ) - 0.5 * EnergyScoreSpread(self.ensemble_dim).compute_chunk(

@@ -90,6 +90,9 @@ PROTOTYPES = {
     'wb2_ens_metrics': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
                                   C.c_int64, _I64P, _I64P, C.POINTER(Weights),
                                   C.c_int, _P]),
+    'wb2_energy_score': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
+                                   C.c_int64, _I64P, _I64P, C.POINTER(Weights),
+                                   _P]),
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
@@ -234,6 +237,16 @@ class Context:
         self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
         int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
         C.byref(w), int(bool(skipna)), _P(out)))
+
+  # -- K3 ---------------------------------------------------------------------
+  def energy_score(self, x: int, t: int, dtype: int, nmember: int,
+                   member_stride: int, off_x: np.ndarray, off_t: np.ndarray,
+                   weights: 'WeightSpec', out: int):
+    w = weights.as_struct()
+    check(self.lib.wb2_energy_score(
+        self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
+        int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
+        C.byref(w), _P(out)))
 
   # -- K5 ---------------------------------------------------------------------
   def regrid_conservative(self, src: int, dst: int, nfield: int,

@@ -265,7 +265,8 @@ def _segments(factors_along_col: np.ndarray):
 
 def build_weights(ctx: _lib.Context, latitude: np.ndarray,
                   longitude: np.ndarray, regions: Sequence, layout: str,
-                  row_stride: int, cell_cache: Optional[dict] = None
+                  row_stride: int, cell_cache: Optional[dict] = None,
+                  max_regions: int = _lib.MAX_REGIONS
                   ) -> list[tuple[list[int], _lib.WeightSpec]]:
   """WeightSpecs for `regions` (entries may be None = global).
 
@@ -282,8 +283,8 @@ def build_weights(ctx: _lib.Context, latitude: np.ndarray,
   out = []
   nlat, nlon = latitude.size, longitude.size
   for key, idx in groups.items():
-    for j0 in range(0, len(idx), _lib.MAX_REGIONS):
-      ids = idx[j0:j0 + _lib.MAX_REGIONS]
+    for j0 in range(0, len(idx), max_regions):
+      ids = idx[j0:j0 + max_regions]
       latf = np.stack([facs[i].lat for i in ids])  # [R, nlat]
       lonf = np.stack([facs[i].lon for i in ids])  # [R, nlon]
       zero_skip = any(regions[i] is not None for i in ids)
@@ -469,6 +470,52 @@ def run_ens_metrics(ctx: _lib.Context, x_ops: Sequence[Operand],
       dims_list.append(dims)
       shape_list.append(shape)
     return stats, dims_list, shape_list, ms
+  finally:
+    for p in staged:
+      ctx.free(p)
+
+
+# ---- K3: energy score --------------------------------------------------------
+ENERGY_MAX_REGIONS = 4
+
+
+def run_energy_score(ctx: _lib.Context, x_ops: Sequence[Operand],
+                     t_ops: Sequence[Operand], ens_dim: str, latitude,
+                     longitude, regions: Sequence, cell_cache=None):
+  """Runs K3.  Returns (stats, dims, M): stats[v] has shape
+  outer_shape[v] + (len(regions), 4, M) -- see wb2_energy_score."""
+  staged: list = []
+  try:
+    first = None
+    stats, dims_list, ms = [], [], []
+    for xo, to in zip(x_ops, t_ops):
+      xo = _to_device_operand(ctx, xo, staged)
+      to = _to_device_operand(ctx, to, staged)
+      xo, m, st = split_member_dim(xo, ens_dim)
+      if first is None:
+        first = xo
+        groups = build_weights(ctx, np.asarray(latitude),
+                               np.asarray(longitude), regions, xo.layout,
+                               xo.row_stride, cell_cache, ENERGY_MAX_REGIONS)
+      dims, shape = broadcast_dims(xo, to)
+      base = min(xo.addr, to.addr)
+      off_x = offset_table(xo, dims, shape) + (xo.addr - base) // 4
+      off_t = offset_table(to, dims, shape) + (to.addr - base) // 4
+      nfield = off_x.size
+      res = np.empty((nfield, len(regions), 4, m), dtype=np.float64)
+      for ids, spec in groups:
+        out_dev = ctx.malloc(nfield * len(ids) * 4 * m * 8)
+        try:
+          ctx.energy_score(base, base, _lib.F32, m, st, off_x, off_t, spec,
+                           out_dev)
+          res[:, ids] = ctx.from_device(out_dev, (nfield, len(ids), 4, m),
+                                        np.float64)
+        finally:
+          ctx.free(out_dev)
+      stats.append(res.reshape(shape + (len(regions), 4, m)))
+      dims_list.append(dims)
+      ms.append(m)
+    return stats, dims_list, ms
   finally:
     for p in staged:
       ctx.free(p)

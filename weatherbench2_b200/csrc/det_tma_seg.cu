@@ -30,6 +30,7 @@ constexpr int kSegConsumerWarps = 8;
 constexpr int kSegThreads = (kSegConsumerWarps + 1) * 32;
 constexpr int kSegTilesInFlight = kSegConsumerWarps / 2;
 constexpr int kSegDump = 8;  // tiles between register -> shared float64 dumps
+constexpr int kSegMaxSpans = 64;  // spans per half row (two rounds of 32 lanes)
 
 struct TmaSegParams {
   const float* f;
@@ -41,6 +42,8 @@ struct TmaSegParams {
   const float* row_wf;       // [R][nrow] float32 copy of row_w
   const float* seg_wf;       // [nseg][RCH] float32, zero padded
   const int32_t* seg_start;  // [nseg + 1]
+  const int4* spans;         // [2][kSegMaxSpans] (first col, end col, segment, -)
+  int32_t nspan[2];          // spans of the left / right half row
   double* partial;           // [ncta][warps][maxslots][R][WB2_DET_NSTAT]
   int64_t ntiles;
   int32_t nrow, ncol;
@@ -160,14 +163,11 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   const int R = p.nregion;
   const bool zero_skip = p.zero_skip != 0;
   const int pair = warp >> 1, half = warp & 1;
-  const int half_cols = (p.ncol + 1) >> 1;
-  const int h0 = half ? half_cols : 0;
-  const int h1 = half ? p.ncol : half_cols;
-  const int span = (((h1 - h0) + 31) >> 5) | 1;  // odd -> conflict-free scalar LDS
-  const int c0 = min(h1, h0 + lane * span);
-  const int c1 = min(h1, c0 + span);
-  int k0 = 0;  // segment of the first column of this lane's span (fixed)
-  while (k0 + 1 < p.nseg && s_segstart[k0 + 1] <= c0) ++k0;
+  // Host-built spans of this half row: contiguous column ranges that never
+  // cross a segment boundary, at most 32 per round (one per lane), so the
+  // region update below is warp-uniform.
+  const int nspan = p.nspan[half];
+  const int4* spans = p.spans + half * kSegMaxSpans;
 
   float accr[RCH][NS];
 #pragma unroll
@@ -238,14 +238,17 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
     const float* st_ = reinterpret_cast<const float*>(src + p.stage_op_bytes);
     const float* sc = reinterpret_cast<const float*>(src + 2 * p.stage_op_bytes);
 
-    float part[NS];
+    mbar_wait(&full[s], use & 1);
+    for (int si = lane; si < nspan; si += 32) {
+      const int4 sp = spans[si];  // x = first column, y = end, z = segment
+      float part[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) part[i] = 0.f;
-    int k = k0;
-    int next_b = s_segstart[k + 1];
-
-    auto apply = [&](int kk) {
-      const float* wv = s_segw + kk * RCH;
+      for (int i = 0; i < NS; ++i) part[i] = 0.f;
+#pragma unroll 4
+      for (int col = sp.x; col < sp.y; ++col)
+        seg_cell<CLIM, SKIPNA>(sf[col], st_[col], CLIM ? sc[col] : 0.f, part);
+      if (!SKIPNA) part[NSUM] = float(sp.y - sp.x);
+      const float* wv = s_segw + sp.z * RCH;
 #pragma unroll
       for (int r = 0; r < RCH; ++r) {
         const float w = u[r] * wv[r];
@@ -254,23 +257,9 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
           for (int i = 0; i < NS; ++i) accr[r][i] = fmaf(w, part[i], accr[r][i]);
         }
       }
-#pragma unroll
-      for (int i = 0; i < NS; ++i) part[i] = 0.f;
-    };
-
-    mbar_wait(&full[s], use & 1);
-    for (int col = c0; col < c1; ++col) {
-      if (col == next_b) {
-        apply(k);
-        ++k;
-        next_b = s_segstart[k + 1];
-      }
-      seg_cell<CLIM, SKIPNA>(sf[col], st_[col], CLIM ? sc[col] : 0.f, part);
-      if (!SKIPNA) part[NSUM] += 1.0f;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
-    if (c1 > c0) apply(k);
 
     if (++since_dump >= kSegDump) dump();
     row += kSegTilesInFlight;
@@ -337,6 +326,37 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
   const int64_t per = (ntiles + ncta - 1) / ncta;
   const int maxslots = static_cast<int>((per + w->nrow - 1) / w->nrow) + 1;
 
+  // Boundary-aligned spans: every segment piece inside a half row is cut into
+  // equal parts no longer than S columns, S the smallest length that keeps the
+  // half row within 32 spans (one per lane); rows with very many tiny segments
+  // take a second round.
+  std::vector<int4> h_spans(2 * kSegMaxSpans, make_int4(0, 0, 0, 0));
+  int h_nspan[2] = {0, 0};
+  const int half_cols = (w->ncol + 1) / 2;
+  for (int half = 0; half < 2; ++half) {
+    const int h0 = half ? half_cols : 0, h1 = half ? w->ncol : half_cols;
+    std::vector<int4> best;
+    for (int limit : {32, kSegMaxSpans}) {
+      for (int S = std::max(1, (h1 - h0 + limit - 1) / limit); S <= h1 - h0; ++S) {
+        std::vector<int4> cur;
+        for (int k = 0; k < w->nseg; ++k) {
+          const int a = std::max(h0, w->seg_start[k]), b = std::min(h1, w->seg_start[k + 1]);
+          if (a >= b) continue;
+          const int parts = (b - a + S - 1) / S;
+          for (int q = 0; q < parts; ++q) {
+            const int c0 = a + int64_t(b - a) * q / parts, c1 = a + int64_t(b - a) * (q + 1) / parts;
+            cur.push_back(make_int4(c0, c1, k, 0));
+          }
+        }
+        if (static_cast<int>(cur.size()) <= limit) { best = cur; break; }
+      }
+      if (!best.empty()) break;
+    }
+    if (best.empty() && h1 > h0) return 0;  // too many segments: LDG path
+    h_nspan[half] = static_cast<int>(best.size());
+    for (size_t i = 0; i < best.size(); ++i) h_spans[half * kSegMaxSpans + i] = best[i];
+  }
+
   for (int r0 = 0; r0 < w->nregion; r0 += rch) {
     const int nreg = std::min(rch, w->nregion - r0);
     // float32 weights of this region chunk
@@ -366,6 +386,7 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
     size_t o1 = pk.add(row_wf.data(), row_wf.size() * sizeof(float));
     size_t o2 = pk.add(seg_wf.data(), seg_wf.size() * sizeof(float));
     size_t o3 = pk.add(w->seg_start, size_t(w->nseg + 1) * sizeof(int32_t));
+    size_t o4 = pk.add(h_spans.data(), h_spans.size() * sizeof(int4));
     WB2_TRY(pk.commit());
 
     TmaSegParams p;
@@ -375,6 +396,8 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
     p.off_f = d_off_f; p.off_t = d_off_t; p.off_c = d_off_c;
     p.row_wf = pk.dev<float>(o1); p.seg_wf = pk.dev<float>(o2);
     p.seg_start = pk.dev<int32_t>(o3);
+    p.spans = pk.dev<int4>(o4);
+    p.nspan[0] = h_nspan[0]; p.nspan[1] = h_nspan[1];
     p.partial = ctx->tma_partial;
     p.ntiles = ntiles;
     p.nrow = w->nrow; p.ncol = w->ncol; p.row_stride = w->row_stride;
