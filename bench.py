@@ -41,6 +41,18 @@ LEVELS = [50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000]
 BYTES_PER_CELL = 12  # f + t + c, float32
 
 
+def _ncu_traffic():
+  """dram bytes per launch of the dominant kernel from the committed ncu
+  capture (profiles/r1_k1_traffic.json); None if absent or another path."""
+  if os.environ.get('WB2_DET_PATH') == 'ldg':
+    return None
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r1_k1_traffic.json')) as fh:
+      return float(json.load(fh)['dram_bytes_per_launch'])
+  except Exception:  # pylint: disable=broad-except
+    return None
+
+
 def _peak_gbs():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   try:
@@ -165,7 +177,7 @@ def run_reference(args):
     return
   import multiprocessing as mp
   cores = os.cpu_count() or 1
-  workers = max(1, min(cores, 64))
+  workers = max(1, min(cores, 256))  # all host cores
   ctxm = mp.get_context('fork')
   with ctxm.Pool(workers) as pool:
     for _ in range(max(1, min(args.warmup, 1))):
@@ -326,7 +338,9 @@ def main():
       'gpu_launches': int(launches),
       'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                    'unit': 'GB/s', 'frac': achieved / peak,
-                   'traffic': args.traffic, 'peak_source': peak_src,
+                   'traffic': (args.traffic if args.traffic is not None
+                               else _ncu_traffic()),
+                   'peak_source': peak_src,
                    'kernel': ('det_metrics_kernel<float,4,CLIM> (LDG path)'
                               if os.environ.get('WB2_DET_PATH') == 'ldg' else
                               'det_tma_kernel<CLIM,!SKIPNA> (TMA ring)') +
