@@ -96,6 +96,33 @@ def bench_ens(args):
     del x, t
 
 
+def bench_energy(args):
+  torch, _lib, ctx = setup()
+  from weatherbench2_b200 import _spatial as sp
+  lat = np.linspace(-90, 90, NLAT)
+  lon = np.arange(NLON) * 0.25
+  for m in args.members:
+    nfield = args.fields
+    x = torch.randn((m, nfield, NLAT, NLON), device='cuda',
+                    dtype=torch.float32)
+    t = torch.randn((nfield, NLAT, NLON), device='cuda', dtype=torch.float32)
+    (_, spec), = sp.build_weights(ctx, lat, lon, [None], 'lat_lon', NLON)
+    slab = NLAT * NLON
+    base = min(x.data_ptr(), t.data_ptr())
+    off_x = np.arange(nfield, dtype=np.int64) * slab + (x.data_ptr() -
+                                                        base) // 4
+    off_t = np.arange(nfield, dtype=np.int64) * slab + (t.data_ptr() -
+                                                        base) // 4
+    out = torch.zeros((nfield, 1, 4, m), device='cuda', dtype=torch.float64)
+    fn = lambda: ctx.energy_score(base, base, _lib.F32, m, nfield * slab,
+                                  off_x, off_t, spec, out.data_ptr())
+    ms = timeit(fn, args.steps)
+    pts = nfield * slab
+    report(f'energy_score M={m}', ms, pts * (4 * m + 4), pts, 'grid_points',
+           {'members': m, 'fields': nfield})
+    del x, t
+
+
 def bench_det(args):
   torch, _lib, ctx = setup()
   from weatherbench2_b200 import _spatial as sp, regions as R
@@ -186,10 +213,10 @@ def bench_spectrum(args):
 if __name__ == '__main__':
   ap = argparse.ArgumentParser()
   ap.add_argument('--kernel', required=True,
-                  choices=['ens', 'det', 'regrid', 'spectrum'])
+                  choices=['ens', 'energy', 'det', 'regrid', 'spectrum'])
   ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--fields', type=int, default=39)
   ap.add_argument('--members', type=int, nargs='+', default=[50])
   a = ap.parse_args()
-  {'ens': bench_ens, 'det': bench_det, 'regrid': bench_regrid,
+  {'ens': bench_ens, 'energy': bench_energy, 'det': bench_det, 'regrid': bench_regrid,
    'spectrum': bench_spectrum}[a.kernel](a)

@@ -130,8 +130,8 @@ __device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float 
   val[1] = spread;
 }
 
-template <int MP, bool SKIPNA, bool EXACT>
-__global__ void __launch_bounds__(kEnsThreads, 4) ens_metrics_kernel(const EnsParams p) {
+template <int MP, bool SKIPNA, bool EXACT, int OCC>
+__global__ void __launch_bounds__(kEnsThreads, OCC) ens_metrics_kernel(const EnsParams p) {
   constexpr int NCNT = SKIPNA ? kEnsStats : 1;
   constexpr int NS = kEnsStats + NCNT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,10 +250,25 @@ static int launch_ens(wb2_ctx* ctx, const EnsParams& p, int64_t nfield, bool ski
     WB2_CUDA_TRY(cudaGetLastError());
     return WB2_OK;
   };
-  if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true>)
-                           : go(ens_metrics_kernel<MP, true, false>);
-  return exact ? go(ens_metrics_kernel<MP, false, true>)
-               : go(ens_metrics_kernel<MP, false, false>);
+  // resident CTAs per SM the register allocation targets (tuning knob)
+  const char* occ_env = getenv("WB2_ENS_OCC");
+  const int occ = occ_env ? atoi(occ_env) : 4;
+  if (occ >= 6) {
+    if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true, 6>)
+                             : go(ens_metrics_kernel<MP, true, false, 6>);
+    return exact ? go(ens_metrics_kernel<MP, false, true, 6>)
+                 : go(ens_metrics_kernel<MP, false, false, 6>);
+  }
+  if (occ == 5) {
+    if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true, 5>)
+                             : go(ens_metrics_kernel<MP, true, false, 5>);
+    return exact ? go(ens_metrics_kernel<MP, false, true, 5>)
+                 : go(ens_metrics_kernel<MP, false, false, 5>);
+  }
+  if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true, 4>)
+                           : go(ens_metrics_kernel<MP, true, false, 4>);
+  return exact ? go(ens_metrics_kernel<MP, false, true, 4>)
+               : go(ens_metrics_kernel<MP, false, false, 4>);
 }
 
 }  // namespace wb2
