@@ -476,7 +476,7 @@ def run_ens_metrics(ctx: _lib.Context, x_ops: Sequence[Operand],
 
 
 # ---- K3: energy score --------------------------------------------------------
-ENERGY_MAX_REGIONS = 4
+ENERGY_MAX_REGIONS = _lib.MAX_REGIONS
 
 
 def run_energy_score(ctx: _lib.Context, x_ops: Sequence[Operand],

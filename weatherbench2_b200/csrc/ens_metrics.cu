@@ -252,7 +252,7 @@ static int launch_ens(wb2_ctx* ctx, const EnsParams& p, int64_t nfield, bool ski
   };
   // resident CTAs per SM the register allocation targets (tuning knob)
   const char* occ_env = getenv("WB2_ENS_OCC");
-  const int occ = occ_env ? atoi(occ_env) : 4;
+  const int occ = occ_env ? atoi(occ_env) : (skipna ? 4 : 5);
   if (occ >= 6) {
     if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true, 6>)
                              : go(ens_metrics_kernel<MP, true, false, 6>);
