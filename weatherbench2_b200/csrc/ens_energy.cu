@@ -36,6 +36,7 @@ struct EsParams {
   int32_t nmember, nrow, ncol, nregion, nseg, zero_skip, rows_per_block, nblk;
   int32_t ngroups;         // ceil(nmember / GS)
   int32_t rows_in_flight;  // warps per CTA / ngroups
+  int32_t vec4;            // 1: every slab / segment is 16-byte aligned
 };
 
 // blockDim = 32 * ngroups * rows_in_flight; warp -> (row slot, member group)
@@ -77,7 +78,39 @@ __global__ void __launch_bounds__(256) energy_kernel(const EsParams p) {
       float acc[NACC];
 #pragma unroll
       for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-      for (int col = s + lane; col < e; col += 32) {
+      int col_begin = s + lane;
+      if (p.vec4 && !weighted) {
+        // 128-bit loads: a lane owns 4 consecutive columns, so four times the
+        // bytes are in flight per load instruction (scalar loads leave this
+        // kernel latency-bound).  Host guarantees 16-byte alignment and
+        // (e - s) % 4 == 0.
+        for (int col = s + lane * 4; col < e; col += 128) {
+          const float* src = px + rbase + col;
+          const float4 t4 = ldg_stream(reinterpret_cast<const float4*>(pt + rbase + col));
+          float4 v[GS + 1];
+#pragma unroll
+          for (int j = 0; j <= GS; ++j)
+            v[j] = (m0 + j) < M
+                       ? ldg_stream(reinterpret_cast<const float4*>(src + int64_t(j) * p.member_stride))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < GS; ++j) {
+            if (m0 + j < M) {
+              const float d0 = v[j].x - t4.x, d1 = v[j].y - t4.y, d2 = v[j].z - t4.z,
+                          d3 = v[j].w - t4.w;
+              acc[j] += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+              if (m0 + j + 1 < M) {
+                const float g0 = v[j].x - v[j + 1].x, g1 = v[j].y - v[j + 1].y,
+                            g2 = v[j].z - v[j + 1].z, g3 = v[j].w - v[j + 1].w;
+                acc[GS + j] += (g0 * g0 + g1 * g1) + (g2 * g2 + g3 * g3);
+              }
+            }
+          }
+          acc[2 * GS] += 4.f;
+        }
+        col_begin = e;  // nothing left for the scalar loop
+      }
+      for (int col = col_begin; col < e; col += 32) {
         float wc = 1.f;
         if (weighted) {
           if (p.col_w) wc *= s_colw[col];
@@ -170,7 +203,7 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
   const int ngroups = (nmember + gs - 1) / gs;  // <= 8
   const int rows_in_flight = std::max(1, 8 / ngroups);
   const int warps = ngroups * rows_in_flight;
-  int rows_per_block = 4 * rows_in_flight;
+  int rows_per_block = 8 * rows_in_flight;
   int nblk = (w->nrow + rows_per_block - 1) / rows_per_block;
   while (nblk * nfield < 4 * ctx->num_sms && rows_per_block > rows_in_flight) {
     rows_per_block = std::max(rows_in_flight, rows_per_block / 2);
@@ -202,6 +235,14 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
   p.nregion = R; p.nseg = w->nseg; p.zero_skip = w->zero_skip;
   p.rows_per_block = rows_per_block; p.nblk = nblk;
   p.ngroups = ngroups; p.rows_in_flight = rows_in_flight;
+  {
+    bool ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(t) & 15) == 0 && member_stride % 4 == 0 &&
+              w->row_stride % 4 == 0;
+    for (int k = 0; k <= w->nseg && ok; ++k) ok = w->seg_start[k] % 4 == 0;
+    for (int64_t i = 0; i < nfield && ok; ++i) ok = off_x[i] % 4 == 0 && off_t[i] % 4 == 0;
+    p.vec4 = ok ? 1 : 0;
+  }
   const size_t smem = w->col_w ? size_t(w->ncol) * sizeof(float) : 0;
   const unsigned grid = static_cast<unsigned>(nfield * nblk);
   if (gs == 4) {
