@@ -178,7 +178,7 @@ int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int dtype,
  *   out   device [nfield][nregion][4][nmember] float64:
  *         [0][m] sum W (x_m - t)^2         [1][m] sum W (x_m - x_{m+1})^2 (m < M-1)
  *         [2][m], [3][m] the matching weight sums
- * NaN propagates (skipna = False semantics); 1..80 members.                     */
+ * NaN propagates (skipna = False semantics); 1..64 members.                     */
 int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                      int32_t nmember, int64_t member_stride, int64_t nfield,
                      const int64_t* off_x, const int64_t* off_t,

@@ -264,7 +264,7 @@ def _energy_k3(forecast: xl.Dataset, truth: xl.Dataset, ens_dim: str, region):
 
 
 def _use_k3(forecast, ens_dim, skipna) -> bool:
-  return (not skipna) and forecast.sizes[ens_dim] <= 80
+  return (not skipna) and forecast.sizes[ens_dim] <= 64
 
 
 @dataclasses.dataclass

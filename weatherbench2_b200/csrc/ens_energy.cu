@@ -41,7 +41,7 @@ struct EsParams {
 
 // blockDim = 32 * ngroups * rows_in_flight; warp -> (row slot, member group)
 template <int GS>
-__global__ void __launch_bounds__(256) energy_kernel(const EsParams p) {
+__global__ void __launch_bounds__(256, 2) energy_kernel(const EsParams p) {
   constexpr int NACC = 2 * GS + 1;  // skill[GS], spread[GS], weight sum
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_colw = reinterpret_cast<float*>(smem_raw);
@@ -190,8 +190,8 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
                                 const wb2_weights* w, double* out) {
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_energy_score: only WB2_F32 inputs are supported");
-  WB2_REQUIRE(nmember >= 1 && nmember <= 80,
-              "wb2_energy_score: 1..80 ensemble members are supported (got %d)", nmember);
+  WB2_REQUIRE(nmember >= 1 && nmember <= 64,
+              "wb2_energy_score: 1..64 ensemble members are supported (got %d)", nmember);
   WB2_TRY(validate_weights(w));
   WB2_REQUIRE(out != nullptr, "out is NULL");
   WB2_REQUIRE(nfield >= 0 && nfield <= (int64_t(1) << 24), "nfield out of range");
@@ -199,7 +199,7 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
   WB2_REQUIRE(x && t && off_x && off_t, "x/t and their offset tables must not be NULL");
   DeviceGuard guard(ctx->device);
 
-  const int gs = nmember <= 4 ? 4 : 10;
+  const int gs = nmember <= 4 ? 4 : 8;
   const int ngroups = (nmember + gs - 1) / gs;  // <= 8
   const int rows_in_flight = std::max(1, 8 / ngroups);
   const int warps = ngroups * rows_in_flight;
@@ -253,10 +253,10 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
     energy_kernel<4><<<grid, 32 * warps, smem, ctx->stream>>>(p);
   } else {
     if (smem > 48 * 1024)
-      WB2_CUDA_TRY(cudaFuncSetAttribute(energy_kernel<10>,
+      WB2_CUDA_TRY(cudaFuncSetAttribute(energy_kernel<8>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    energy_kernel<10><<<grid, 32 * warps, smem, ctx->stream>>>(p);
+    energy_kernel<8><<<grid, 32 * warps, smem, ctx->stream>>>(p);
   }
   WB2_CUDA_TRY(cudaGetLastError());
   energy_finalize_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(

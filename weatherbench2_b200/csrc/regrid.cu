@@ -65,16 +65,30 @@ __global__ void __launch_bounds__(kRgThreads) regrid_kernel(const RegridParams p
     wtab[i] = p.grp_w[size_t(g) * p.maxnb * kRgGroup + i];
   for (int i = threadIdx.x; i < nb; i += kRgThreads) rows[i] = p.grp_rows[size_t(g) * p.maxnb + i];
   __syncthreads();
+  float* s_wsum = reinterpret_cast<float*>(rows + p.maxnb);  // [G] weight row sums
+  if (threadIdx.x < kRgGroup) {
+    float ws = 0.f;
+    for (int bi = 0; bi < nb; ++bi) ws = fmaf(wtab[bi * kRgGroup + threadIdx.x], 1.f, ws);
+    s_wsum[threadIdx.x] = ws;
+  }
+  __syncthreads();
 
   const float* __restrict__ x = p.src + field * p.src_field_stride;
   const float nanv = __int_as_float(0x7fc00000);
 
   // ---- stage 1: contract over source longitude, every source row read once ---
+  // The valid-weight sum v = sum_b W[a,b] [x[b,d] not NaN] equals the plain row
+  // sum of the weights unless a NaN is met, so the hot loop only accumulates y
+  // and remembers whether its column saw a NaN; columns that did recompute v
+  // exactly (second pass over the same rows, served by L1/L2).
   float y[kRgDpt][kRgGroup], v[kRgDpt][kRgGroup];
+  bool saw_nan[kRgDpt];
 #pragma unroll
-  for (int i = 0; i < kRgDpt; ++i)
+  for (int i = 0; i < kRgDpt; ++i) {
+    saw_nan[i] = false;
 #pragma unroll
-    for (int a = 0; a < kRgGroup; ++a) { y[i][a] = 0.f; v[i][a] = 0.f; }
+    for (int a = 0; a < kRgGroup; ++a) y[i][a] = 0.f;
+  }
 
 #pragma unroll 4
   for (int bi = 0; bi < nb; ++bi) {
@@ -90,12 +104,31 @@ __global__ void __launch_bounds__(kRgThreads) regrid_kernel(const RegridParams p
 #pragma unroll
     for (int i = 0; i < kRgDpt; ++i) {
       const bool ok = xv[i] == xv[i];
+      saw_nan[i] |= !ok;
       const float x0 = ok ? xv[i] : 0.f;
-      const float one = ok ? 1.f : 0.f;
 #pragma unroll
-      for (int a = 0; a < kRgGroup; ++a) {
-        y[i][a] = fmaf(w[a], x0, y[i][a]);
-        v[i][a] = fmaf(w[a], one, v[i][a]);
+      for (int a = 0; a < kRgGroup; ++a) y[i][a] = fmaf(w[a], x0, y[i][a]);
+    }
+  }
+  // v for NaN-free columns: the weights' row sums, added in the same order and
+  // rounding as the explicit accumulation would (bit-identical)
+  float wsum[kRgGroup];
+#pragma unroll
+  for (int a = 0; a < kRgGroup; ++a) wsum[a] = s_wsum[a];
+#pragma unroll
+  for (int i = 0; i < kRgDpt; ++i) {
+#pragma unroll
+    for (int a = 0; a < kRgGroup; ++a) v[i][a] = wsum[a];
+    if (saw_nan[i]) {
+      const int d = threadIdx.x + i * kRgThreads;
+#pragma unroll
+      for (int a = 0; a < kRgGroup; ++a) v[i][a] = 0.f;
+      for (int bi = 0; bi < nb; ++bi) {
+        const float xv = __ldg(x + int64_t(rows[bi]) * p.nlat_s + d);
+        const float one = xv == xv ? 1.f : 0.f;
+#pragma unroll
+        for (int a = 0; a < kRgGroup; ++a)
+          v[i][a] = fmaf(wtab[bi * kRgGroup + a], one, v[i][a]);
       }
     }
   }
@@ -229,7 +262,7 @@ extern "C" int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* ds
   p.nlon_t = lon_w->n_tgt; p.nlat_t = lat_w->n_tgt;
   p.ngroups = ngroups; p.maxnb = maxnb;
   const size_t smem = (size_t(kRgGroup) * 2 * p.nlat_s + size_t(maxnb) * kRgGroup) * sizeof(float) +
-                      size_t(maxnb) * sizeof(int);
+                      size_t(maxnb) * sizeof(int) + kRgGroup * sizeof(float);
   WB2_REQUIRE(smem <= 200 * 1024, "wb2_regrid_conservative: weights too dense for shared memory");
   const int dpt = (p.nlat_s + kRgThreads - 1) / kRgThreads;
   auto go = [&](auto kernel) -> int {
