@@ -476,6 +476,38 @@ def test_acc_with_dayofyear_climatology():
                 ).compute_chunk(fds, tds)
 
 
+def test_shared_dims_are_joined_by_label():
+  """`forecast - truth` aligns shared dimensions by coordinate label (xarray's
+  inner join): by-valid forecasts whose `time` is a subset / reordering of the
+  truth's.  The join is an offset-table gather, no data is copied."""
+  from weatherbench2_b200 import metrics, xarray_lite as xl
+  rs = np.random.RandomState(12)
+  lat, lon = _grid(19, 36)
+  t_times = np.arange(10)
+  f_times = np.array([7, 2, 3, 11, 5])  # 11 is not in truth
+  dims = ('time', 'level', 'latitude', 'longitude')
+  f = rs.normal(size=(5, 2, 19, 36)).astype(np.float32)
+  t = rs.normal(size=(10, 2, 19, 36)).astype(np.float32)
+  coords = {'level': np.array([500, 850]), 'latitude': lat, 'longitude': lon}
+  fds = xl.Dataset({'z': (dims, f)}, dict(coords, time=f_times))
+  tds = xl.Dataset({'z': (dims, t)}, dict(coords, time=t_times))
+  got = metrics.MSE().compute_chunk(fds, tds)['z']
+  keep = [0, 1, 2, 4]
+  want, wd = orc.mse(f[keep], dims, t[[7, 2, 3, 5]], dims, lat, lon)
+  assert got.dims == wd and got.shape == (4, 2)
+  np.testing.assert_array_equal(got.coords['time'].values, [7, 2, 3, 5])
+  np.testing.assert_allclose(got.values, want, rtol=RTOL)
+  # ensemble path too
+  x = rs.normal(size=(3, 5, 2, 19, 36)).astype(np.float32)
+  eds = xl.Dataset({'z': (('realization',) + dims, x)},
+                   dict(coords, time=f_times, realization=np.arange(3)))
+  got = metrics.CRPS().compute_chunk(eds, tds)['z']
+  want, wd = orc.crps(x[:, keep], ('realization',) + dims, t[[7, 2, 3, 5]],
+                      dims, 'realization', lat, lon)
+  a, b, _ = orc.align(got.values, got.dims, want, wd)
+  np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
 def test_non_increasing_latitude_raises():
   from weatherbench2_b200 import metrics, xarray_lite as xl
   lat = np.array([45.0, 0.0, -45.0])

@@ -50,6 +50,7 @@ def _ens_stats(forecast: xl.Dataset, truth: xl.Dataset, ens_dim: str,
     f_da, t_da = forecast[name], truth[name]
     if LAT not in f_da.dims or LON not in f_da.dims:
       continue
+    f_da, t_da = xl.align_inner(f_da, t_da)
     # K2 computes in float32 (float64 inputs are rounded to float32 first)
     x_op = sp.prepare_operand(f_da, None, np.float32)
     t_op = sp.prepare_operand(t_da, x_op.layout, np.float32)
@@ -243,6 +244,7 @@ def _energy_k3(forecast: xl.Dataset, truth: xl.Dataset, ens_dim: str, region):
     f_da, t_da = forecast[name], truth[name]
     if LAT not in f_da.dims or LON not in f_da.dims:
       continue
+    f_da, t_da = xl.align_inner(f_da, t_da)
     x_op = sp.prepare_operand(f_da, None, np.float32)
     t_op = sp.prepare_operand(t_da, x_op.layout, np.float32)
     (st,), (dims,), (mm,) = sp.run_energy_score(

@@ -394,6 +394,22 @@ def split_member_dim(op: Operand, ens_dim: str):
       op, outer_dims=tuple(op.outer_dims[k] for k in keep),
       outer_shape=tuple(op.outer_shape[k] for k in keep),
       outer_strides=tuple(op.outer_strides[k] for k in keep))
+  terms = getattr(op, 'gather_terms', None)
+  if terms is not None:
+    # a gathered operand addresses through explicit (dims, offsets) terms: the
+    # member axis must be a plain strided term
+    rest = []
+    for tdims, arr in terms:
+      if ens_dim in tdims:
+        if tdims != (ens_dim,):
+          raise ValueError('the ensemble dimension cannot be part of a gather')
+        arr = np.asarray(arr)
+        stride = int(arr[1] - arr[0]) if arr.size > 1 else 0
+        if arr.size > 2 and not (np.diff(arr) == stride).all():
+          raise ValueError('ensemble members must be evenly strided')
+      else:
+        rest.append((tdims, arr))
+    out.gather_terms = rest
   return out, int(m), int(stride)
 
 

@@ -75,66 +75,7 @@ def select_truth_at_valid_time(truth: xl.Dataset, forecast: xl.Dataset
   return out
 
 
-class LazyGather(xl.DataArray):
-  """A DataArray view `source.isel(dim=positions)` with N-d positions, not
-  materialised unless `.values` is read.  `_spatial.prepare_operand` turns it
-  into offset-table addressing."""
-
-  def __init__(self, source: xl.DataArray, index_maps: dict,
-               extra_coords: t.Optional[dict] = None):
-    dims, shape = [], []
-    for d, n in source.sizes.items():
-      if d in index_maps:
-        tdims, pos = index_maps[d]
-        for td, tn in zip(tdims, np.asarray(pos).shape):
-          if td not in dims:
-            dims.append(td)
-            shape.append(tn)
-      else:
-        dims.append(d)
-        shape.append(n)
-    self._source = source
-    self._index_maps = {d: (tuple(td), np.asarray(p, dtype=np.int64))
-                        for d, (td, p) in index_maps.items()}
-    self._lazy_dims = tuple(dims)
-    self._lazy_shape = tuple(shape)
-    self._materialised = None
-    self.dims = tuple(dims)
-    self.name = source.name
-    self.attrs = dict(source.attrs)
-    self.coords = {k: c for k, c in source.coords.items()
-                   if not any(d in index_maps for d in c.dims)}
-    for k, c in (extra_coords or {}).items():
-      self.coords[k] = c
-
-  @property
-  def lazy_source(self):
-    return self._source, self._index_maps
-
-  @property
-  def shape(self):
-    return self._lazy_shape
-
-  @property
-  def _data(self):
-    if self._materialised is None:
-      v = self._source.values
-      sdims = list(self._source.dims)
-      for d, (tdims, pos) in self._index_maps.items():
-        ax = sdims.index(d)
-        v = np.take(v, pos, axis=ax)
-        sdims[ax:ax + 1] = list(tdims)
-      perm = [sdims.index(d) for d in self._lazy_dims]
-      self._materialised = np.transpose(v, perm)
-    return self._materialised
-
-  @_data.setter
-  def _data(self, value):  # DataArray.__init__ is bypassed
-    self._materialised = value
-
-  @property
-  def dtype(self):
-    return self._source.dtype
+LazyGather = xl.LazyGather  # defined next to the container it extends
 
 
 def _metric_and_region_loop(forecast: xl.Dataset, truth: xl.Dataset,

@@ -189,6 +189,8 @@ def _det_stats(forecast: xl.Dataset, truth: xl.Dataset, climatology,
     f_da, t_da = forecast[name], truth[name]
     if LAT not in f_da.dims or LON not in f_da.dims:
       continue
+    # xarray arithmetic joins shared dimensions by label (inner join)
+    f_da, t_da = xl.align_inner(f_da, t_da)
     f_op = sp.prepare_operand(f_da)
     t_op = sp.prepare_operand(t_da, f_op.layout, f_op.dtype)
     if t_op.row_stride != f_op.row_stride or t_op.on_device != f_op.on_device:

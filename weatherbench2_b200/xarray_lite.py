@@ -925,3 +925,94 @@ def to_xarray(obj):
 
 def is_native_xarray(obj) -> bool:
   return type(obj).__module__.startswith('xarray')
+
+
+class LazyGather(DataArray):
+  """A DataArray view `source.isel(dim=positions)` with N-d positions, not
+  materialised unless `.values` is read.  `_spatial.prepare_operand` turns it
+  into offset-table addressing."""
+
+  def __init__(self, source: DataArray, index_maps: dict,
+               extra_coords: Optional[dict] = None):
+    dims, shape = [], []
+    for d, n in source.sizes.items():
+      if d in index_maps:
+        tdims, pos = index_maps[d]
+        for td, tn in zip(tdims, np.asarray(pos).shape):
+          if td not in dims:
+            dims.append(td)
+            shape.append(tn)
+      else:
+        dims.append(d)
+        shape.append(n)
+    self._source = source
+    self._index_maps = {d: (tuple(td), np.asarray(p, dtype=np.int64))
+                        for d, (td, p) in index_maps.items()}
+    self._lazy_dims = tuple(dims)
+    self._lazy_shape = tuple(shape)
+    self._materialised = None
+    self.dims = tuple(dims)
+    self.name = source.name
+    self.attrs = dict(source.attrs)
+    self.coords = {k: c for k, c in source.coords.items()
+                   if not any(d in index_maps for d in c.dims)}
+    for k, c in (extra_coords or {}).items():
+      self.coords[k] = c
+
+  @property
+  def lazy_source(self):
+    return self._source, self._index_maps
+
+  @property
+  def shape(self):
+    return self._lazy_shape
+
+  @property
+  def _data(self):
+    if self._materialised is None:
+      v = self._source.values
+      sdims = list(self._source.dims)
+      for d, (tdims, pos) in self._index_maps.items():
+        ax = sdims.index(d)
+        v = np.take(v, pos, axis=ax)
+        sdims[ax:ax + 1] = list(tdims)
+      perm = [sdims.index(d) for d in self._lazy_dims]
+      self._materialised = np.transpose(v, perm)
+    return self._materialised
+
+  @_data.setter
+  def _data(self, value):  # DataArray.__init__ is bypassed
+    self._materialised = value
+
+  @property
+  def dtype(self):
+    return self._source.dtype
+
+
+def align_inner(a: DataArray, b: DataArray):
+  """xarray's default arithmetic alignment (join='inner') of two arrays along
+  the dimensions they share: labels present in both, in the order of `a`.
+  Returns the inputs untouched when the shared coordinates already agree;
+  otherwise lazily gathered views (no data copied)."""
+  maps_a, maps_b = {}, {}
+  for d in a.dims:
+    if d not in b.dims or d not in a.coords or d not in b.coords:
+      continue
+    ca, cb = a.coords[d].values, b.coords[d].values
+    if ca.shape == cb.shape and np.array_equal(ca, cb):
+      continue
+    keep = np.isin(ca, cb)
+    labels = ca[keep]
+    maps_a[d] = ((d,), np.nonzero(keep)[0])
+    maps_b[d] = ((d,), _lookup(cb, labels))
+  if not maps_a:
+    return a, b
+
+  def view(x, maps):
+    if hasattr(x, 'lazy_source'):  # nested gathers: materialise the inner one
+      x = DataArray(x.values, x.dims, x.coords, x.name, x.attrs)
+    extra = {d: Coord((d,), x.coords[d].values[pos])
+             for d, (_, pos) in maps.items()}
+    return LazyGather(x, maps, extra_coords=extra)
+
+  return view(a, maps_a), view(b, maps_b)
