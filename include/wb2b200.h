@@ -166,6 +166,9 @@ int wb2_det_metrics_host(wb2_ctx* ctx, const void* f, const void* t,
  *   member_stride elements between consecutive members of the same cell
  *   t, off_t     truth slab per field
  *   out          device [nfield][nregion][WB2_ENS_NSTAT] float64
+ * 1..64 members: register sorting networks (the fast path); 65..1551 members
+ * (metrics_test.py uses 100 and 1000): rank by counting in shared memory;
+ * more: WB2_EUNSUPPORTED.
  */
 int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                     int32_t nmember, int64_t member_stride, int64_t nfield,

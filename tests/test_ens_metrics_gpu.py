@@ -269,12 +269,59 @@ def test_regions_lon_lat_layout_and_device_inputs():
            want, wd, rtol=RTOL, atol=1e-6)
 
 
+@pytest.mark.parametrize('ensemble_size,skipna', [(65, False), (100, False),
+                                                  (100, True), (1000, False)])
+def test_large_ensembles_rank_by_counting(ensemble_size, skipna):
+  """More than 64 members take the rank-by-counting kernel (ens_big.cu); the
+  reference's tests use 100 and 1000 (metrics_test.py:785-789, 857-861)."""
+  from weatherbench2_b200 import metrics, regions as R
+  fds, tds, forecast, truth, lat, lon = _pair(
+      ensemble_size=ensemble_size, lead_stop='1 day',
+      time_stop='2019-12-01T12', spatial_resolution_in_degrees=30)
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  f = f.copy()
+  # ties, and (skipna) missing members
+  f[(slice(None),) + (0,) * (f.ndim - 1)] = np.round(
+      f[(slice(None),) + (0,) * (f.ndim - 1)], 0)
+  if skipna:
+    rs = np.random.RandomState(3)
+    f[rs.uniform(size=f.shape) < 0.05] = np.nan
+  forecast['vars']['geopotential'] = (fd, f)
+  fds = _ds(forecast['vars'], forecast['coords'])
+  args = (f, fd, t, tdm, 'realization', lat, lon)
+  preg = [None, R.SliceRegion(lat_slice=slice(-30, 60))]
+  oreg = [None, orc.SliceRegion(lat_slice=slice(-30, 60))]
+  for p, o in zip(preg, oreg):
+    want, wd = orc.crps(*args, region=o, skipna=skipna)
+    _cmp(metrics.CRPS().compute_chunk(fds, tds, region=p,
+                                      skipna=skipna)['geopotential'],
+         want, wd, rtol=RTOL, atol=1e-6)
+    want, wd = orc.crps_spread(f, fd, 'realization', lat, lon, region=o,
+                               skipna=skipna)
+    _cmp(metrics.CRPSSpread().compute_chunk(fds, tds, region=p,
+                                            skipna=skipna)['geopotential'],
+         want, wd, rtol=RTOL, atol=1e-6)
+  want, wd = orc.ensemble_variance(f, fd, 'realization', lat, lon,
+                                   skipna=skipna)
+  _cmp(metrics.EnsembleVariance().compute_chunk(fds, tds, skipna=skipna)[
+      'geopotential'], want, wd, rtol=RTOL)
+  want, wd = orc.ensemble_mean_mse(*args, skipna=skipna)
+  _cmp(metrics.EnsembleMeanMSE().compute_chunk(fds, tds, skipna=skipna)[
+      'geopotential'], want, wd, rtol=RTOL, atol=1e-6)
+
+
 def test_too_many_members_raises_loudly():
-  from weatherbench2_b200 import _lib, metrics
-  fds, tds, *_ = _pair(ensemble_size=65, lead_stop='0 day',
-                       time_stop='2019-12-01T03')
-  with pytest.raises(_lib.Wb2Error):
-    metrics.CRPS().compute_chunk(fds, tds)
+  from weatherbench2_b200 import _lib, _spatial as sp
+  ctx = _lib.default_context(0)
+  lat = np.linspace(-90, 90, 4)
+  lon = np.linspace(0, 360, 8, endpoint=False)
+  (_, spec), = sp.build_weights(ctx, lat, lon, [None], 'lat_lon', 8)
+  off = np.zeros(1, dtype=np.int64)
+  buf = ctx.malloc(4096)
+  with pytest.raises(_lib.Wb2Error, match='at most'):
+    ctx.ens_metrics(buf, buf, _lib.F32, 5000, 0, off, off, spec, False, buf)
+  ctx.free(buf)
 
 
 def test_missing_ensemble_dim_raises():

@@ -125,6 +125,11 @@ struct DeviceGuard {
 
 int validate_weights(const wb2_weights* w);
 
+// ens_big.cu: ensembles of more than 64 members (rank by counting).
+int ens_metrics_big(wb2_ctx* ctx, const float* x, const float* t, int32_t nmember,
+                    int64_t member_stride, int64_t nfield, const int64_t* off_x,
+                    const int64_t* off_t, const wb2_weights* w, int skipna, double* out);
+
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -282,14 +282,15 @@ extern "C" int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int d
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_metrics: only WB2_F32 inputs are supported");
   WB2_REQUIRE(nmember >= 1, "wb2_ens_metrics: nmember must be >= 1");
-  WB2_REQUIRE(nmember <= 64,
-              "wb2_ens_metrics: at most 64 ensemble members are supported (got %d)", nmember);
   WB2_TRY(validate_weights(w));
   WB2_REQUIRE(out != nullptr, "out is NULL");
   WB2_REQUIRE(nfield >= 0 && nfield <= (int64_t(1) << 24), "nfield out of range");
   if (nfield == 0) return WB2_OK;
   WB2_REQUIRE(x && t && off_x && off_t, "x/t and their offset tables must not be NULL");
   DeviceGuard guard(ctx->device);
+  if (nmember > 64)  // rank-by-counting path (ens_big.cu)
+    return ens_metrics_big(ctx, static_cast<const float*>(x), static_cast<const float*>(t),
+                           nmember, member_stride, nfield, off_x, off_t, w, skipna, out);
 
   int rows_per_block = 2 * kEnsWarps;
   int nblk = (w->nrow + rows_per_block - 1) / rows_per_block;
