@@ -36,6 +36,11 @@ struct BigParams {
   int32_t skipna;
 };
 
+// floats of the [M][33] tile, rounded up so the float64 area behind it is aligned
+__host__ __device__ inline size_t big_tile_floats(int nmember) {
+  return (size_t(nmember) * kBigPitch + 3) & ~size_t(3);
+}
+
 __device__ __forceinline__ bool big_less(float a, int ia, float b, int ib) {
   // total order of np.argsort (stable; NaN sorts last)
   const bool an = a != a, bn = b != b;
@@ -46,7 +51,7 @@ __device__ __forceinline__ bool big_less(float a, int ia, float b, int ib) {
 __global__ void __launch_bounds__(kBigThreads) ens_big_kernel(const BigParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                 // [M][33]
-  double* red = reinterpret_cast<double*>(tile + size_t(p.nmember) * kBigPitch);
+  double* red = reinterpret_cast<double*>(tile + big_tile_floats(p.nmember));
   // red: [warps][32 regions][10]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -156,7 +161,7 @@ __global__ void ens_big_finalize_kernel(const double* __restrict__ partial,
 int ens_metrics_big(wb2_ctx* ctx, const float* x, const float* t, int32_t nmember,
                     int64_t member_stride, int64_t nfield, const int64_t* off_x,
                     const int64_t* off_t, const wb2_weights* w, int skipna, double* out) {
-  const size_t smem = size_t(nmember) * kBigPitch * sizeof(float) +
+  const size_t smem = big_tile_floats(nmember) * sizeof(float) +
                       size_t(kBigWarps) * 32 * WB2_ENS_NSTAT * sizeof(double);
   if (smem > 220 * 1024) {
     set_error("wb2_ens_metrics: at most %d ensemble members are supported (got %d)",
