@@ -210,13 +210,66 @@ def bench_spectrum(args):
          'grid_cells')
 
 
+def bench_maps(args):
+  """K6 / K6e: Spatial* maps; per-time maps (ngroup 1) and a 10-step time mean
+  fused in (ngroup 10)."""
+  torch, _lib, ctx = setup()
+  slab = NLAT * NLON
+  nfield = 390  # 10 times x 39 (variable, level) maps
+  f = torch.randn((nfield, NLAT, NLON), device='cuda', dtype=torch.float32)
+  t = torch.randn((nfield, NLAT, NLON), device='cuda', dtype=torch.float32)
+  base = min(f.data_ptr(), t.data_ptr())
+  for ngroup in (1, 10):
+    nout = nfield // ngroup
+    # group-major tables: output j averages times g of (variable, level) j
+    idx = (np.arange(ngroup)[None, :] * nout + np.arange(nout)[:, None])
+    off_f = (idx * slab + (f.data_ptr() - base) // 4).astype(np.int64).ravel()
+    off_t = (idx * slab + (t.data_ptr() - base) // 4).astype(np.int64).ravel()
+    out = torch.empty((nout, NLAT, NLON), device='cuda', dtype=torch.float32)
+    fn = lambda: ctx.det_maps(base, base, _lib.F32, _lib.MAP_MSE, nout, ngroup,
+                              off_f, off_t, NLAT, NLON, NLON, False,
+                              out.data_ptr())
+    ms = timeit(fn, args.steps)
+    cells = nfield * slab
+    report(f'det_maps MSE ngroup={ngroup}', ms, cells * 8 + nout * slab * 4,
+           cells, 'grid_cells')
+  del f, t
+  for m in args.members:
+    ntime, nmap = 5, 8
+    x = torch.randn((m, ntime * nmap, NLAT, NLON), device='cuda',
+                    dtype=torch.float32)
+    t = torch.randn((ntime * nmap, NLAT, NLON), device='cuda',
+                    dtype=torch.float32)
+    base = min(x.data_ptr(), t.data_ptr())
+    for ngroup, mask in ((1, _lib.ENS_CRPS), (ntime, _lib.ENS_CRPS),
+                         (ntime, 63)):
+      nout = ntime * nmap // ngroup
+      idx = (np.arange(ngroup)[None, :] * nout + np.arange(nout)[:, None])
+      off_x = (idx * slab + (x.data_ptr() - base) // 4).astype(
+          np.int64).ravel()
+      off_t = (idx * slab + (t.data_ptr() - base) // 4).astype(
+          np.int64).ravel()
+      nsel = bin(mask).count('1')
+      out = torch.empty((nsel, nout, NLAT, NLON), device='cuda',
+                        dtype=torch.float32)
+      fn = lambda: ctx.ens_maps(base, base, _lib.F32, m, ntime * nmap * slab,
+                                nout, ngroup, off_x, off_t, NLAT, NLON, NLON,
+                                mask, False, out.data_ptr())
+      ms = timeit(fn, args.steps)
+      pts = ntime * nmap * slab
+      report(f'ens_maps M={m} ngroup={ngroup} nsel={nsel}', ms,
+             pts * (4 * m + 4) + nsel * nout * slab * 4, pts, 'grid_points')
+    del x, t
+
+
 if __name__ == '__main__':
   ap = argparse.ArgumentParser()
   ap.add_argument('--kernel', required=True,
-                  choices=['ens', 'energy', 'det', 'regrid', 'spectrum'])
+                  choices=['ens', 'energy', 'det', 'regrid', 'spectrum',
+                           'maps'])
   ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--fields', type=int, default=39)
   ap.add_argument('--members', type=int, nargs='+', default=[50])
   a = ap.parse_args()
   {'ens': bench_ens, 'energy': bench_energy, 'det': bench_det, 'regrid': bench_regrid,
-   'spectrum': bench_spectrum}[a.kernel](a)
+   'spectrum': bench_spectrum, 'maps': bench_maps}[a.kernel](a)

@@ -187,6 +187,38 @@ int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                      const int64_t* off_x, const int64_t* off_t,
                      const wb2_weights* w, double* out);
 
+/* ---- K6: map-output ("Spatial*") metrics with the time mean fused in ---------
+ * Replaces SpatialBias / SpatialMSE / SpatialMAE .compute_chunk
+ * (metrics.py:304-374) and the `.mean(time, skipna)` of Metric.compute
+ * (metrics.py:117-138): out[j] = mean_g stat(f[j*ngroup+g], t[j*ngroup+g]) per
+ * grid cell.  ngroup == 1 gives the per-time maps of compute_chunk unchanged.
+ *   stat        WB2_MAP_BIAS f - t | WB2_MAP_MSE (f - t)^2 | WB2_MAP_MAE |f - t|
+ *   off_f/off_t host [nout * ngroup] element offsets of the slabs (group-major)
+ *   nrow, ncol, row_stride   slab geometry (col contiguous)
+ *   skipna      mean over the non-NaN terms (NaN when there is none)
+ *   out         device [nout][nrow][ncol], same element type as the inputs    */
+enum { WB2_MAP_BIAS = 0, WB2_MAP_MSE = 1, WB2_MAP_MAE = 2 };
+int wb2_det_maps(wb2_ctx* ctx, const void* f, const void* t, int dtype, int stat,
+                 int64_t nout, int32_t ngroup, const int64_t* off_f,
+                 const int64_t* off_t, int32_t nrow, int32_t ncol,
+                 int64_t row_stride, int skipna, void* out);
+
+/* Ensemble variant: SpatialCRPS / SpatialCRPSSkill / SpatialCRPSSpread
+ * (metrics.py:718-772), SpatialEnsembleVariance (:1244-1266),
+ * SpatialEnsembleMeanMSE / DebiasedSpatialEnsembleMeanMSE (:1366-1399) and the
+ * time mean of EnsembleMetric.compute (:598-607).  One read of the members
+ * yields every selected map.
+ *   stat_mask   bit i selects point-wise statistic i of WB2_ENS_NSTAT's list
+ *               (0 skill, 1 spread, 2 (t - xbar)^2, 3 variance, 4 debiased MSE);
+ *               bit 5 = point-wise CRPS, skill - spread / 2 (metrics.py:729-739)
+ *   out         device [popcount(stat_mask)][nout][nrow][ncol] float32, in
+ *               increasing bit order; 1..64 members                            */
+int wb2_ens_maps(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                 int32_t nmember, int64_t member_stride, int64_t nout,
+                 int32_t ngroup, const int64_t* off_x, const int64_t* off_t,
+                 int32_t nrow, int32_t ncol, int64_t row_stride,
+                 int32_t stat_mask, int skipna, float* out);
+
 /* ---- K5: conservative regridding -------------------------------------------
  * Replaces ConservativeRegridder.regrid_array (= _nanmean,
  * weatherbench2/regridding.py:502-536).  The two weight matrices

@@ -697,3 +697,47 @@ def zonal_energy_spectrum(x, dims, lat, lon):
   shape[ilat] = len(lat)
   spectrum = spectrum * circumference(lat).reshape(shape)
   return spectrum, out_dims, frequency, wavelength
+
+
+# ---------------------------------------------------------------------------
+# Map-output ("Spatial*") metrics: no spatial averaging (metrics.py:304-374,
+# 718-772, 1244-1266, 1366-1399); Metric.compute then averages over time
+# (metrics.py:117-138).
+# ---------------------------------------------------------------------------
+def spatial_det_map(stat, f, fdims, t, tdims):
+  """stat in {'bias', 'mse', 'mae'}: forecast - truth, squared, absolute."""
+  fa, ta, d = align(f, fdims, t, tdims)
+  diff = fa - ta
+  if stat == "bias":
+    return diff, d  # metrics.py:374
+  if stat == "mse":
+    return diff ** 2, d  # metrics.py:316
+  if stat == "mae":
+    return np.abs(diff), d  # metrics.py:345
+  raise ValueError(stat)
+
+
+def spatial_ens_maps(f, fdims, t, tdims, ens_dim, skipna):
+  """Point-wise ensemble statistics {name: (map, dims)}."""
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  n = f.shape[ax]
+  od = tuple(x for x in fdims if x != ens_dim)
+  skill, sd = pointwise_crps_skill(f, fdims, t, tdims, ens_dim, skipna)
+  spread, pd_ = pointwise_crps_spread(f, fdims, ens_dim, skipna)
+  m = _mean(f, ax, skipna)
+  ta, ma, d = align(t, tdims, m, od)
+  mse = (ta - ma) ** 2  # metrics.py:1381
+  if n == 1:
+    var = np.zeros_like(m)  # metrics.py:1257-1264
+    var_for_debias = _var(f, ax, skipna)
+  else:
+    var = _var(f, ax, skipna)  # metrics.py:1266
+    var_for_debias = var
+  ba, va, d2 = align(mse, d, var_for_debias, od)
+  sa, pa, d3 = align(skill, sd, spread, pd_)
+  return {
+      "skill": (skill, sd), "spread": (spread, pd_), "mse": (mse, d),
+      "variance": (var, od), "debiased": (ba - va / n, d2),
+      "crps": (sa - 0.5 * pa, d3),  # metrics.py:729-739
+  }

@@ -327,3 +327,122 @@ class EnergyScore(EnsembleMetric):
         forecast, truth, region=region, skipna=skipna
     ) - 0.5 * EnergyScoreSpread(self.ensemble_dim).compute_chunk(
         forecast, truth, region=region, skipna=skipna)
+
+
+# ------------------------------------------------------------------------------
+# Map-output ("Spatial*") ensemble metrics: K6e (csrc/ens_maps.cu)
+# ------------------------------------------------------------------------------
+_MAP_BITS = (_lib.ENS_SKILL, _lib.ENS_SPREAD, _lib.ENS_MEAN_SE,
+             _lib.ENS_VARIANCE, _lib.ENS_DEBIASED, _lib.ENS_CRPS)
+_ALL_MAPS = sum(_MAP_BITS)
+
+
+def _ens_maps(forecast: xl.Dataset, truth: xl.Dataset, ens_dim: str,
+              stat_mask: int, reduce_dim: t.Optional[str], skipna: bool) -> dict:
+  """{var: (maps[nsel, ...], dims, coords, M)} for the selected statistics."""
+  ctx = m._context()  # pylint: disable=protected-access
+  out = {}
+  for name in m._common_vars(forecast, truth):  # pylint: disable=protected-access
+    f_da, t_da = forecast[name], truth[name]
+    if LAT not in f_da.dims or LON not in f_da.dims:
+      continue
+    f_da, t_da = xl.align_inner(f_da, t_da)
+    x_op = sp.prepare_operand(f_da, None, np.float32)
+    t_op = sp.prepare_operand(t_da, x_op.layout, np.float32)
+    maps, dims, mm = sp.run_ens_maps(ctx, x_op, t_op, ens_dim, stat_mask,
+                                     reduce_dim, skipna)
+    coords = m._map_coords(dims, f_da, t_da)  # pylint: disable=protected-access
+    coords.pop(ens_dim, None)
+    out[name] = (maps, dims, coords, mm)
+  return out
+
+
+def _ens_map_request(forecast, truth, ens_dim, bit, reduce_dim, skipna):
+  """One statistic's maps; inside `metrics.batch()` all six come from a single
+  pass over the ensemble and are shared by the Spatial* metrics."""
+  b = m._batch  # pylint: disable=protected-access
+  if b.active:
+    key = ('ensmap', id(forecast), id(truth), ens_dim, reduce_dim,
+           bool(skipna))
+    if key not in b.cache:
+      b.cache[key] = (_ens_maps(forecast, truth, ens_dim, _ALL_MAPS,
+                                reduce_dim, skipna), forecast, truth)
+    res, sel = b.cache[key][0], _MAP_BITS.index(bit)
+  else:
+    res, sel = _ens_maps(forecast, truth, ens_dim, bit, reduce_dim, skipna), 0
+  out = xl.Dataset()
+  for name, (maps, dims, coords, _) in res.items():
+    out[name] = xl.DataArray(maps[sel], dims, coords, name)
+  return out
+
+
+@dataclasses.dataclass
+class _SpatialEnsembleMetric(EnsembleMetric):
+  """Base of the map-output ensemble metrics: `compute_chunk` gives the
+  per-time maps, `compute` fuses the time mean into the kernel."""
+
+  def _maps(self, forecast, truth, reduce_dim, skipna):
+    forecast, truth, native = m._prep(forecast, truth)  # pylint: disable=protected-access
+    n_ensemble = _get_n_ensemble(forecast, self.ensemble_dim)
+    ds = _ens_map_request(forecast, truth, self.ensemble_dim, self._BIT,
+                          reduce_dim, skipna)
+    if n_ensemble == 1 and self._ZERO_FOR_SINGLE_MEMBER:
+      # metrics.py:1257-1264: zeros_like(forecast).mean(ensemble_dim)
+      for name in list(ds.keys()):
+        da = ds[name]
+        ds[name] = xl.DataArray(xl.zeros_like(da).data, da.dims, da.coords,
+                                name)
+    return m._finish(ds, native)  # pylint: disable=protected-access
+
+  def compute_chunk(self, forecast, truth, region=None, skipna=False):
+    del region  # ignored, like the reference
+    return self._maps(forecast, truth, None, skipna)
+
+  def compute(self, forecast, truth, region=None, skipna=False):
+    del region
+    fc = xl.from_xarray(forecast)
+    result = self._maps(forecast, truth, m._avg_dim(fc), skipna)  # pylint: disable=protected-access
+    return result.assign_attrs(ensemble_size=fc.sizes[self.ensemble_dim])
+
+
+@dataclasses.dataclass
+class SpatialCRPS(_SpatialEnsembleMetric):
+  """CRPS without spatial averaging (metrics.py:718-739)."""
+  _BIT = _lib.ENS_CRPS
+  _ZERO_FOR_SINGLE_MEMBER = False
+
+
+@dataclasses.dataclass
+class SpatialCRPSSpread(_SpatialEnsembleMetric):
+  """CRPSSpread without spatial averaging (metrics.py:742-754)."""
+  _BIT = _lib.ENS_SPREAD
+  _ZERO_FOR_SINGLE_MEMBER = False
+
+
+@dataclasses.dataclass
+class SpatialCRPSSkill(_SpatialEnsembleMetric):
+  """CRPSSkill without spatial averaging (metrics.py:757-772)."""
+  _BIT = _lib.ENS_SKILL
+  _ZERO_FOR_SINGLE_MEMBER = False
+
+
+@dataclasses.dataclass
+class SpatialEnsembleVariance(_SpatialEnsembleMetric):
+  """Ensemble variance without spatial averaging (metrics.py:1244-1266)."""
+  _BIT = _lib.ENS_VARIANCE
+  _ZERO_FOR_SINGLE_MEMBER = True
+
+
+@dataclasses.dataclass
+class SpatialEnsembleMeanMSE(_SpatialEnsembleMetric):
+  """Squared error of the ensemble mean per grid cell (metrics.py:1366-1381)."""
+  _BIT = _lib.ENS_MEAN_SE
+  _ZERO_FOR_SINGLE_MEMBER = False
+
+
+@dataclasses.dataclass
+class DebiasedSpatialEnsembleMeanMSE(_SpatialEnsembleMetric):
+  """Debiased squared error of the ensemble mean per grid cell
+  (metrics.py:1384-1399)."""
+  _BIT = _lib.ENS_DEBIASED
+  _ZERO_FOR_SINGLE_MEMBER = False

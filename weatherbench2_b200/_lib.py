@@ -19,6 +19,10 @@ F32, F64 = 0, 1
 MAX_REGIONS = 32
 DET_NSTAT = 10
 ENS_NSTAT = 10
+MAP_BIAS, MAP_MSE, MAP_MAE = 0, 1, 2
+# bits of wb2_ens_maps' stat_mask
+ENS_SKILL, ENS_SPREAD, ENS_MEAN_SE, ENS_VARIANCE, ENS_DEBIASED = 1, 2, 4, 8, 16
+ENS_CRPS = 32
 
 
 class Wb2Error(RuntimeError):
@@ -93,6 +97,12 @@ PROTOTYPES = {
     'wb2_energy_score': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
                                    C.c_int64, _I64P, _I64P, C.POINTER(Weights),
                                    _P]),
+    'wb2_det_maps': (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int64,
+                               C.c_int32, _I64P, _I64P, C.c_int32, C.c_int32,
+                               C.c_int64, C.c_int, _P]),
+    'wb2_ens_maps': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
+                               C.c_int64, C.c_int32, _I64P, _I64P, C.c_int32,
+                               C.c_int32, C.c_int64, C.c_int32, C.c_int, _P]),
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
@@ -247,6 +257,27 @@ class Context:
         self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
         int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
         C.byref(w), _P(out)))
+
+  # -- K6 ---------------------------------------------------------------------
+  def det_maps(self, f: int, t: int, dtype: int, stat: int, nout: int,
+               ngroup: int, off_f: np.ndarray, off_t: np.ndarray, nrow: int,
+               ncol: int, row_stride: int, skipna: bool, out: int):
+    assert off_f.size == nout * ngroup and off_t.size == nout * ngroup
+    check(self.lib.wb2_det_maps(
+        self.handle, _P(f), _P(t), dtype, int(stat), int(nout), int(ngroup),
+        _as_ptr(off_f, C.c_int64), _as_ptr(off_t, C.c_int64), int(nrow),
+        int(ncol), int(row_stride), int(bool(skipna)), _P(out)))
+
+  def ens_maps(self, x: int, t: int, dtype: int, nmember: int,
+               member_stride: int, nout: int, ngroup: int, off_x: np.ndarray,
+               off_t: np.ndarray, nrow: int, ncol: int, row_stride: int,
+               stat_mask: int, skipna: bool, out: int):
+    assert off_x.size == nout * ngroup and off_t.size == nout * ngroup
+    check(self.lib.wb2_ens_maps(
+        self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
+        int(nout), int(ngroup), _as_ptr(off_x, C.c_int64),
+        _as_ptr(off_t, C.c_int64), int(nrow), int(ncol), int(row_stride),
+        int(stat_mask), int(bool(skipna)), _P(out)))
 
   # -- K5 ---------------------------------------------------------------------
   def regrid_conservative(self, src: int, dst: int, nfield: int,

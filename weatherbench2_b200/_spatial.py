@@ -535,3 +535,128 @@ def run_energy_score(ctx: _lib.Context, x_ops: Sequence[Operand],
   finally:
     for p in staged:
       ctx.free(p)
+
+
+# ---- K6: map-output metrics (time mean fused in) -------------------------------
+def _grouped_tables(ops: Sequence[Operand], reduce_dim: Optional[str]):
+  """Offset tables of `ops` over their broadcast outer grid with `reduce_dim`
+  (if present) moved last: returns (tables, out_dims, out_shape, ngroup)."""
+  dims, shape = broadcast_dims(*ops)
+  if reduce_dim is not None and reduce_dim in dims:
+    i = dims.index(reduce_dim)
+    ngroup = shape[i]
+    out_dims = dims[:i] + dims[i + 1:]
+    out_shape = shape[:i] + shape[i + 1:]
+    dims, shape = out_dims + (reduce_dim,), out_shape + (ngroup,)
+  else:
+    ngroup, out_dims, out_shape = 1, dims, shape
+  return ([offset_table(op, dims, shape) for op in ops], out_dims, out_shape,
+          ngroup)
+
+
+def _map_dims(op: Operand):
+  return (LAT, LON) if op.layout == 'lat_lon' else (LON, LAT)
+
+
+def _alloc_maps(ctx: _lib.Context, like: Operand, shape: tuple, dtype):
+  """Device buffer for the output maps: a torch tensor when the inputs are
+  torch CUDA tensors (the result stays on the device), else a raw allocation
+  that `_fetch_maps` copies back."""
+  if xl._is_torch(like.data):  # pylint: disable=protected-access
+    import torch  # pylint: disable=import-outside-toplevel
+    out = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name),
+                      device=like.data.device)
+    return out, int(out.data_ptr())
+  nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+  return None, ctx.malloc(max(nbytes, 16))
+
+
+def _fetch_maps(ctx: _lib.Context, tensor, ptr: int, shape: tuple, dtype):
+  if tensor is not None:
+    return tensor
+  try:
+    return ctx.from_device(ptr, shape, dtype)
+  finally:
+    ctx.free(ptr)
+
+
+def run_det_maps(ctx: _lib.Context, f_op: Operand, t_op: Operand, stat: int,
+                 reduce_dim: Optional[str], skipna: bool):
+  """Runs K6 for one variable: maps of stat(f, t) averaged over `reduce_dim`
+  (None: no averaging).  Returns (maps, dims)."""
+  staged: list = []
+  try:
+    was_dev = f_op.on_device
+    f_op = _to_device_operand(ctx, f_op, staged)
+    t_op = _to_device_operand(ctx, t_op, staged)
+    if (t_op.layout != f_op.layout or t_op.row_stride != f_op.row_stride or
+        t_op.nrow != f_op.nrow or t_op.ncol != f_op.ncol or
+        t_op.dtype != f_op.dtype):
+      raise ValueError('forecast and truth must share dtype, layout and grid')
+    (off_f, off_t), out_dims, out_shape, ngroup = _grouped_tables(
+        [f_op, t_op], reduce_dim)
+    es = f_op.itemsize
+    base = min(f_op.addr, t_op.addr)
+    off_f = off_f + (f_op.addr - base) // es
+    off_t = off_t + (t_op.addr - base) // es
+    nout = off_f.size // ngroup
+    shape = tuple(out_shape) + (f_op.nrow, f_op.ncol)
+    tensor, ptr = _alloc_maps(ctx, f_op if was_dev else t_op, shape,
+                              f_op.dtype)
+    code = _lib.F32 if f_op.dtype == np.float32 else _lib.F64
+    try:
+      ctx.det_maps(base, base, code, stat, nout, ngroup, off_f, off_t,
+                   f_op.nrow, f_op.ncol, f_op.row_stride, skipna, ptr)
+    except Exception:
+      if tensor is None:
+        ctx.free(ptr)
+      raise
+    maps = _fetch_maps(ctx, tensor, ptr, shape, f_op.dtype)
+    return maps, tuple(out_dims) + _map_dims(f_op)
+  finally:
+    for p in staged:
+      ctx.free(p)
+
+
+def run_ens_maps(ctx: _lib.Context, x_op: Operand, t_op: Operand,
+                 ens_dim: str, stat_mask: int, reduce_dim: Optional[str],
+                 skipna: bool):
+  """Runs K6e for one variable.  Returns (maps[nsel, ...], dims, M): the
+  selected point-wise ensemble statistics (increasing bit order of
+  `stat_mask`) averaged over `reduce_dim`."""
+  staged: list = []
+  try:
+    if ens_dim in t_op.outer_dims:
+      raise ValueError(f'truth must not have the {ens_dim!r} dimension')
+    was_dev = x_op.on_device
+    x_op = _to_device_operand(ctx, x_op, staged)
+    t_op = _to_device_operand(ctx, t_op, staged)
+    x_op, m, st = split_member_dim(x_op, ens_dim)
+    if (t_op.layout != x_op.layout or t_op.row_stride != x_op.row_stride or
+        t_op.nrow != x_op.nrow or t_op.ncol != x_op.ncol):
+      raise ValueError('forecast and truth must share layout and grid')
+    if x_op.dtype != np.float32 or t_op.dtype != np.float32:
+      raise ValueError('ensemble kernels take float32 operands')
+    (off_x, off_t), out_dims, out_shape, ngroup = _grouped_tables(
+        [x_op, t_op], reduce_dim)
+    base = min(x_op.addr, t_op.addr)
+    off_x = off_x + (x_op.addr - base) // 4
+    off_t = off_t + (t_op.addr - base) // 4
+    nout = off_x.size // ngroup
+    nsel = bin(stat_mask).count('1')
+    shape = (nsel,) + tuple(out_shape) + (x_op.nrow, x_op.ncol)
+    tensor, ptr = _alloc_maps(ctx, x_op if was_dev else t_op, shape,
+                              np.float32)
+    try:
+      ctx.ens_maps(base, base, _lib.F32, m, st, nout, ngroup, off_x, off_t,
+                   x_op.nrow, x_op.ncol, x_op.row_stride, stat_mask, skipna,
+                   ptr)
+    except Exception:
+      if tensor is None:
+        ctx.free(ptr)
+      raise
+    maps = _fetch_maps(ctx, tensor, ptr, shape, np.float32)
+    return maps, tuple(out_dims) + _map_dims(x_op), m
+  finally:
+    for p in staged:
+      ctx.free(p)

@@ -20,22 +20,12 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "ens_point.cuh"
 
 namespace wb2 {
 
-#define CE(a, b)                          \
-  {                                       \
-    const float lo_ = fminf(v[a], v[b]);  \
-    const float hi_ = fmaxf(v[a], v[b]);  \
-    v[a] = lo_;                           \
-    v[b] = hi_;                           \
-  }
-#include "sort_networks.inc"
-#undef CE
-
 constexpr int kEnsWarps = 4;
 constexpr int kEnsThreads = kEnsWarps * 32;
-constexpr int kEnsStats = 5;
 
 struct EnsParams {
   const float* x;
@@ -57,78 +47,6 @@ struct EnsParams {
   int32_t rows_per_block;
   int32_t nblk;
 };
-
-// Point-wise statistics of one grid point.  x[m] for m >= M is padding.
-template <int MP, bool SKIPNA, bool EXACT>
-__device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float (&val)[kEnsStats]) {
-  const float nanf_ = __int_as_float(0x7fc00000);
-  const float inf_ = __int_as_float(0x7f800000);
-  float sumx = 0.f, suma = 0.f;
-  float nvalid = 0.f, navalid = 0.f;
-#pragma unroll
-  for (int m = 0; m < MP; ++m) {
-    if (EXACT || m < M) {
-      const float xm = v[m];
-      const float a = fabsf(t - xm);  // metrics.py:824
-      if (SKIPNA) {
-        if (xm == xm) { sumx += xm; nvalid += 1.f; }
-        if (a == a) { suma += a; navalid += 1.f; }
-      } else {
-        sumx += xm;
-        suma += a;
-      }
-    }
-  }
-  const float fm = float(M);
-  const float mean = SKIPNA ? sumx / nvalid : sumx / fm;  // 0/0 -> NaN like nanmean
-  float ss = 0.f;
-#pragma unroll
-  for (int m = 0; m < MP; ++m) {
-    if (EXACT || m < M) {
-      const float dx = v[m] - mean;
-      if (SKIPNA) {
-        if (dx == dx) ss += dx * dx;
-      } else {
-        ss += dx * dx;
-      }
-    }
-  }
-  float var;
-  if (SKIPNA) var = nvalid > 1.f ? ss / (nvalid - 1.f) : nanf_;  // np.nanvar(ddof=1)
-  else var = ss / (fm - 1.f);                                    // M == 1 -> 0/0 = NaN
-  const float dm = t - mean;
-  const float mse = dm * dm;
-  val[0] = SKIPNA ? suma / navalid : suma / fm;
-  val[2] = mse;
-  val[3] = var;
-  val[4] = mse - var / fm;  // metrics.py:564-565 (always divides by the full M)
-
-  // ---- spread: ranks via sorting network (metrics.py:804-813) ---------------
-  if (M < 2) {
-    val[1] = 0.f;  // metrics.py:788-789
-    return;
-  }
-#pragma unroll
-  for (int m = 0; m < MP; ++m) {
-    if (!EXACT && m >= M) v[m] = inf_;          // padding sorts last
-    else if (SKIPNA && !(v[m] == v[m])) v[m] = inf_;  // NaN sorts last (np.argsort)
-  }
-  SortNet<MP>::run(v);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < MP; ++i) {
-    // coefficient 2 r - M - 1 with r = i + 1
-    const float coef = float(2 * (i + 1)) - fm - 1.f;
-    if (SKIPNA) {
-      if (float(i) < nvalid) s += coef * v[i];
-    } else if (EXACT || i < M) {
-      s += coef * v[i];
-    }
-  }
-  float spread = SKIPNA ? 2.f * (s / nvalid) / (fm - 1.f) : 2.f * (s / fm) / (fm - 1.f);
-  if (!SKIPNA && !(sumx == sumx)) spread = nanf_;  // a NaN member poisons the point
-  val[1] = spread;
-}
 
 template <int MP, bool SKIPNA, bool EXACT, int OCC>
 __global__ void __launch_bounds__(kEnsThreads, OCC) ens_metrics_kernel(const EnsParams p) {

@@ -451,35 +451,73 @@ class Bias(Metric):
         res, lambda st: _ratio(st[..., 2], st[..., 6])), native)
 
 
-def _spatial_variant_not_built(name):
-  raise NotImplementedError(
-      f'{name}: the map-output (Spatial*) metrics are elementwise kernels with '
-      'a device-side time mean; they are the next scope row (SURVEY.md section '
-      '8f) and are not built yet.  There is deliberately no NumPy fallback.')
+def _map_coords(out_dims, *sources: xl.DataArray) -> dict:
+  """Coordinates (latitude / longitude included) that survive in a map."""
+  coords = {}
+  for s in sources:
+    for k, c in s.coords.items():
+      if all(d in out_dims for d in c.dims) and k not in coords:
+        coords[k] = c
+  return coords
+
+
+def _avg_dim(forecast) -> str:
+  if 'time' in forecast.dims:
+    return 'time'
+  if 'init_time' in forecast.dims:
+    return 'init_time'
+  raise ValueError(
+      f'Forecast has neither valid_time or init_time dimension {forecast}')
 
 
 @dataclasses.dataclass
-class SpatialMSE(Metric):
-  """MSE without spatial averaging (metrics.py:304-316) -- not built yet."""
+class _SpatialDetMetric(Metric):
+  """Map-output metrics: K6 (`wb2_det_maps`) computes stat(f, t) per grid cell
+  and, in `compute`, the time mean in the same pass, so the per-time maps are
+  never materialised.  `region` is ignored like in the reference."""
+
+  def _maps(self, forecast, truth, reduce_dim, skipna):
+    forecast, truth, native = _prep(forecast, truth)
+    ctx = _context()
+    out = xl.Dataset()
+    for name in _common_vars(forecast, truth):
+      f_da, t_da = forecast[name], truth[name]
+      if LAT not in f_da.dims or LON not in f_da.dims:
+        continue
+      f_da, t_da = xl.align_inner(f_da, t_da)
+      f_op = sp.prepare_operand(f_da)
+      t_op = sp.prepare_operand(t_da, f_op.layout, f_op.dtype)
+      maps, dims = sp.run_det_maps(ctx, f_op, t_op, self._STAT, reduce_dim,
+                                   skipna)
+      out[name] = xl.DataArray(maps, dims, _map_coords(dims, f_da, t_da), name)
+    return _finish(out, native)
 
   def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_variant_not_built('SpatialMSE')
+    del region, skipna  # ignored (metrics.py:315, 344, 373)
+    return self._maps(forecast, truth, None, False)
+
+  def compute(self, forecast, truth, region=None, skipna=False):
+    """metrics.py:117-138 with the time mean fused into the kernel."""
+    del region
+    return self._maps(forecast, truth, _avg_dim(forecast), skipna)
 
 
 @dataclasses.dataclass
-class SpatialMAE(Metric):
-  """MAE without spatial averaging (metrics.py:333-345) -- not built yet."""
-
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_variant_not_built('SpatialMAE')
+class SpatialMSE(_SpatialDetMetric):
+  """MSE without spatial averaging (metrics.py:304-316)."""
+  _STAT = _lib.MAP_MSE
 
 
 @dataclasses.dataclass
-class SpatialBias(Metric):
-  """Bias without spatial averaging (metrics.py:362-374) -- not built yet."""
+class SpatialMAE(_SpatialDetMetric):
+  """MAE without spatial averaging (metrics.py:333-345)."""
+  _STAT = _lib.MAP_MAE
 
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_variant_not_built('SpatialBias')
+
+@dataclasses.dataclass
+class SpatialBias(_SpatialDetMetric):
+  """Bias without spatial averaging (metrics.py:362-374)."""
+  _STAT = _lib.MAP_BIAS
 
 
 @dataclasses.dataclass
@@ -513,4 +551,6 @@ from weatherbench2_b200._ensemble import (  # noqa: E402  pylint: disable=wrong-
     CRPS, CRPSSkill, CRPSSpread, DebiasedEnsembleMeanMSE, EnergyScore,
     EnergyScoreSkill, EnergyScoreSpread, EnsembleMeanMSE,
     EnsembleMeanRMSESqrtBeforeTimeAvg, EnsembleMetric,
-    EnsembleStddevSqrtBeforeTimeAvg, EnsembleVariance, _get_n_ensemble)
+    EnsembleStddevSqrtBeforeTimeAvg, EnsembleVariance, SpatialCRPS,
+    SpatialCRPSSkill, SpatialCRPSSpread, SpatialEnsembleMeanMSE,
+    SpatialEnsembleVariance, DebiasedSpatialEnsembleMeanMSE, _get_n_ensemble)
