@@ -219,6 +219,48 @@ int wb2_ens_maps(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                  int32_t nrow, int32_t ncol, int64_t row_stride,
                  int32_t stat_mask, int skipna, float* out);
 
+/* ---- K7: threshold ("binary event") and Gaussian-forecast metrics -------------
+ * wb2_ens_threshold_metrics replaces EnsembleBrierScore /
+ * DebiasedEnsembleBrierScore (metrics.py:1523-1710), EnsembleIgnoranceScore
+ * (:1713-1790) and EnsembleRPS (:1793-1891) .compute_chunk: one read of the
+ * members yields all four point-wise scores for every threshold.
+ * Thresholds, two forms:
+ *   thr_b == NULL  thr_a is a float32 threshold field per (threshold, field):
+ *                  off_a host [nthreshold][nfield]  (QuantileThreshold,
+ *                  thresholds.py:118-149)
+ *   thr_b != NULL  thr_a / thr_b are the climatological mean / std slabs,
+ *                  off_a / off_b host [nfield], z host [nthreshold] =
+ *                  norm.ppf(quantile): thr = mean + z * std in float64
+ *                  (GaussianQuantileThreshold, thresholds.py:152-185)
+ *   out   device [nfield][nthreshold][nregion][8] float64:
+ *         [0] sum W*brier  [1] sum W*debiased brier  [2] sum W*ignorance
+ *         [3] sum W*rps part   [4..7] the matching weight sums
+ * Any number of members (streamed, not held in registers).                      */
+int wb2_ens_threshold_metrics(wb2_ctx* ctx, const void* x, const void* t,
+                              int dtype, int32_t nmember, int64_t member_stride,
+                              int64_t nfield, const int64_t* off_x,
+                              const int64_t* off_t, int32_t nthreshold,
+                              const void* thr_a, const int64_t* off_a,
+                              const void* thr_b, const int64_t* off_b,
+                              const double* z, const wb2_weights* w, int skipna,
+                              double* out);
+
+/* wb2_gaussian_metrics replaces GaussianCRPS / GaussianVariance
+ * (metrics.py:849-937) when nthreshold == 0:
+ *         out [nfield][1][nregion][8]: [0] sum W*crps [1] sum W*std^2, [4],[5] weights
+ * and GaussianBrierScore / GaussianIgnoranceScore / GaussianRPS (:963-1158)
+ * when nthreshold > 0 (thresholds as above):
+ *         out [nfield][nthreshold][nregion][8]: [0] brier [2] ignorance [3] rps part
+ * Point-wise math in float64 (the reference calls scipy.stats.norm in float64). */
+int wb2_gaussian_metrics(wb2_ctx* ctx, const void* mean, const void* std,
+                         const void* t, int dtype, int64_t nfield,
+                         const int64_t* off_mean, const int64_t* off_std,
+                         const int64_t* off_t, int32_t nthreshold,
+                         const void* thr_a, const int64_t* off_a,
+                         const void* thr_b, const int64_t* off_b,
+                         const double* z, const wb2_weights* w, int skipna,
+                         double* out);
+
 /* ---- K5: conservative regridding -------------------------------------------
  * Replaces ConservativeRegridder.regrid_array (= _nanmean,
  * weatherbench2/regridding.py:502-536).  The two weight matrices

@@ -741,3 +741,84 @@ def spatial_ens_maps(f, fdims, t, tdims, ens_dim, skipna):
       "variance": (var, od), "debiased": (ba - va / n, d2),
       "crps": (sa - 0.5 * pa, d3),  # metrics.py:729-739
   }
+
+
+# ---------------------------------------------------------------------------
+# Gaussian-forecast and threshold metrics -- metrics.py:849-1158, 1523-1891,
+# thresholds.py:152-185.  Point-wise scores on arrays that already broadcast
+# against each other; callers apply spatial_average / time_mean.
+# ---------------------------------------------------------------------------
+def gaussian_quantile_threshold(clim_mean, clim_std, quantile):
+  """thresholds.py:182-184 (np.float64 scalar * float32 array -> float64)."""
+  from scipy import stats
+  return clim_mean + np.float64(stats.norm.ppf(quantile)) * np.asarray(
+      clim_std, dtype=np.float64)
+
+
+def gaussian_crps_pointwise(f, s, t):
+  """metrics.py:889-899."""
+  from scipy import stats
+  with np.errstate(invalid="ignore", divide="ignore"):
+    norm_diff = (f - t) / s
+    return s * (norm_diff * (2 * stats.norm.cdf(norm_diff) - 1)
+                + 2 * stats.norm.pdf(norm_diff) - 1 / np.sqrt(np.pi))
+
+
+def gaussian_brier_pointwise(f, s, t, thr):
+  """metrics.py:963-980."""
+  from scipy import stats
+  with np.errstate(invalid="ignore", divide="ignore"):
+    truth_probability = np.where(t > thr, 1.0, 0.0)
+    exceedance = 1 - stats.norm.cdf((thr - f) / s)
+    return (exceedance - truth_probability) ** 2
+
+
+def gaussian_ignorance_pointwise(f, s, t, thr):
+  """metrics.py:1029-1049."""
+  from scipy import stats
+  with np.errstate(invalid="ignore", divide="ignore"):
+    truth_probability = np.where(t > thr, 1.0, 0.0)
+    cdf = stats.norm.cdf((thr - f) / s)
+    return -np.where(truth_probability.astype(bool), np.log(1 - cdf),
+                     np.log(cdf))
+
+
+def gaussian_rps_part_pointwise(f, s, t, thr):
+  """metrics.py:1098-1118."""
+  from scipy import stats
+  with np.errstate(invalid="ignore", divide="ignore"):
+    truth_ecdf = np.where(t < thr, 1.0, 0.0)
+    cdf = stats.norm.cdf((thr - f) / s)
+    return (cdf - truth_ecdf) ** 2
+
+
+def ens_brier_pointwise(x, t, thr, ax, debias, skipna):
+  """metrics.py:1523-1560; x has the member axis `ax`, t / thr do not."""
+  te, the = np.expand_dims(t, ax), np.expand_dims(thr, ax)
+  truth_probability = np.where(np.isnan(t), np.nan, np.where(t > thr, 1.0, 0.0))
+  forecast_probability = np.where(np.isnan(x), np.nan,
+                                  np.where(x > the, 1.0, 0.0))
+  del te
+  mean = _mean(forecast_probability, ax, skipna)
+  biased = (mean - truth_probability) ** 2
+  if not debias:
+    return biased
+  var = _var(forecast_probability, ax, skipna)
+  # metrics.py:562-565 (note: truth - mean, squared: same value)
+  return biased - var / x.shape[ax]
+
+
+def ens_ignorance_pointwise(x, t, thr, ax, skipna):
+  """metrics.py:1713-1729."""
+  truth_probability = np.where(t > thr, 1.0, 0.0)
+  forecast_probability = np.where(x > np.expand_dims(thr, ax), 1.0, 0.0)
+  p = _mean(forecast_probability, ax, skipna)
+  with np.errstate(divide="ignore"):
+    return -np.where(truth_probability.astype(bool), np.log(p), np.log(1 - p))
+
+
+def ens_rps_part_pointwise(x, t, thr, ax, skipna):
+  """metrics.py:1793-1803."""
+  truth_ecdf = np.where(t < thr, 1.0, 0.0)
+  forecast_ecdf = np.where(x < np.expand_dims(thr, ax), 1.0, 0.0)
+  return (_mean(forecast_ecdf, ax, skipna) - truth_ecdf) ** 2

@@ -519,3 +519,80 @@ def test_slice_region_mean_subset():
   sub = x[:, ilat][:, :, ilon]
   exp = (sub * w[None, :, None]).sum(axis=(1, 2)) / (w.sum() * ilon.size)
   np.testing.assert_allclose(r, exp, rtol=1e-12)
+
+
+# ---- Gaussian / threshold metrics: the reference's known answers -------------
+# weatherbench2/metrics_test.py:284-304, 368-532, 987-1030, 1292-1390 (mock data
+# are constant fields, so the point-wise score IS the expected average).
+def test_gaussian_crps_known_answer():
+  got = orc.gaussian_crps_pointwise(np.float32(1.0), np.float32(1.0),
+                                    np.float32(1.02))
+  np.testing.assert_allclose(got, 0.23385455, rtol=1e-6)
+
+
+@pytest.mark.parametrize('error,expected_1,expected_2',
+                         [(0.02, 0.04421, 0.257883), (1e6, 0.70786, 0.707861)])
+def test_gaussian_brier_known_answers(error, expected_1, expected_2):
+  f = s = np.float32(1.0 + error)
+  t = np.float32(1.0)
+  thr = orc.gaussian_quantile_threshold(np.float32(1.0), np.float32(1.0), 0.8)
+  np.testing.assert_allclose(orc.gaussian_brier_pointwise(f, s, t, thr),
+                             expected_1, rtol=1e-4)
+  np.testing.assert_allclose(
+      orc.gaussian_brier_pointwise(f, s, t, np.float32(1.0)), expected_2,
+      rtol=1e-4)
+
+
+@pytest.mark.parametrize('error,expected', [(0.02, 0.236055), (1e6, 1.841019)])
+def test_gaussian_ignorance_known_answers(error, expected):
+  f = s = np.float32(1.0 + error)
+  thr = orc.gaussian_quantile_threshold(np.float32(1.0), np.float32(1.0), 0.8)
+  np.testing.assert_allclose(
+      orc.gaussian_ignorance_pointwise(f, s, np.float32(1.0), thr), expected,
+      rtol=1e-4)
+
+
+@pytest.mark.parametrize('error,expected', [(0.02, 0.295746), (1e6, 0.758203)])
+def test_gaussian_rps_known_answers(error, expected):
+  f = s = np.float32(1.0 + error)
+  got = sum(orc.gaussian_rps_part_pointwise(f, s, np.float32(1.0),
+                                            np.float32(q))
+            for q in (0.0, 1.0, 2.0))
+  np.testing.assert_allclose(got, expected, rtol=1e-4)
+
+
+@pytest.mark.parametrize('error,ens_delta,expected',
+                         [(0.0, 0.1, 0.0), (0.0, 1.0, 0.25), (-10.0, 0.1, 1.0)])
+def test_ensemble_brier_known_answers(error, ens_delta, expected):
+  x = (1.0 + error + ens_delta * np.arange(-2, 2)).astype(np.float32)
+  thr = orc.gaussian_quantile_threshold(np.float32(1.0), np.float32(1.0), 0.2)
+  got = orc.ens_brier_pointwise(x, np.float32(1.0), thr, 0, False, False)
+  np.testing.assert_allclose(got, expected, rtol=1e-4, atol=1e-12)
+
+
+def test_ensemble_ignorance_and_rps_known_answers():
+  thr = orc.gaussian_quantile_threshold(np.float32(1.0), np.float32(1.0), 0.2)
+  x = np.full(4, 1.0, np.float32)
+  assert orc.ens_ignorance_pointwise(x, np.float32(1.0), thr, 0, False) == 0
+  assert np.isinf(orc.ens_ignorance_pointwise(x - 10, np.float32(1.0), thr, 0,
+                                              False))
+  for error, expected in ((0.02, 0.0), (-2.0, 2.0)):
+    x = np.full(4, 1.0 + error, np.float32)
+    got = sum(orc.ens_rps_part_pointwise(x, np.float32(1.5), np.float32(q), 0,
+                                         False) for q in (0.0, 1.0, 2.0))
+    assert got == expected
+
+
+def test_debiased_brier_integrates_to_crps():
+  """metrics_test.py:1207-1289: the integral over thresholds of the debiased
+  Brier score of a 2-member ensemble equals its (fair) CRPS."""
+  rs = np.random.RandomState(0)
+  x = rs.normal(size=(2, 400))
+  t = rs.normal(size=400)
+  grid = np.linspace(-6, 6, 4001)
+  bs = np.stack([orc.ens_brier_pointwise(x, t, np.full(400, g), 0, True, False)
+                 for g in grid])
+  integral = np.trapezoid(bs, grid, axis=0).mean()
+  skill = np.abs(x - t).mean()
+  spread = np.abs(x[0] - x[1]).mean()
+  np.testing.assert_allclose(integral, skill - 0.5 * spread, rtol=5e-3)

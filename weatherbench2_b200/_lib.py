@@ -103,6 +103,14 @@ PROTOTYPES = {
     'wb2_ens_maps': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32, C.c_int64,
                                C.c_int64, C.c_int32, _I64P, _I64P, C.c_int32,
                                C.c_int32, C.c_int64, C.c_int32, C.c_int, _P]),
+    'wb2_ens_threshold_metrics': (C.c_int, [
+        _P, _P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int64, _I64P, _I64P,
+        C.c_int32, _P, _I64P, _P, _I64P, C.POINTER(C.c_double),
+        C.POINTER(Weights), C.c_int, _P]),
+    'wb2_gaussian_metrics': (C.c_int, [
+        _P, _P, _P, _P, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_int32,
+        _P, _I64P, _P, _I64P, C.POINTER(C.c_double), C.POINTER(Weights),
+        C.c_int, _P]),
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
@@ -278,6 +286,48 @@ class Context:
         int(nout), int(ngroup), _as_ptr(off_x, C.c_int64),
         _as_ptr(off_t, C.c_int64), int(nrow), int(ncol), int(row_stride),
         int(stat_mask), int(bool(skipna)), _P(out)))
+
+  # -- K7 ---------------------------------------------------------------------
+  @staticmethod
+  def _threshold_args(nthreshold, thr_a, off_a, thr_b, off_b, z):
+    zz = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+    return (int(nthreshold), _P(thr_a) if thr_a else None,
+            _as_ptr(off_a, C.c_int64) if off_a is not None else None,
+            _P(thr_b) if thr_b else None,
+            _as_ptr(off_b, C.c_int64) if off_b is not None else None,
+            _as_ptr(zz, C.c_double) if zz is not None else None), zz
+
+  def ens_threshold_metrics(self, x: int, t: int, nmember: int,
+                            member_stride: int, off_x: np.ndarray,
+                            off_t: np.ndarray, nthreshold: int, thr_a: int,
+                            off_a: np.ndarray, thr_b: Optional[int],
+                            off_b: Optional[np.ndarray],
+                            z: Optional[np.ndarray], weights: 'WeightSpec',
+                            skipna: bool, out: int):
+    w = weights.as_struct()
+    targs, keep = self._threshold_args(nthreshold, thr_a, off_a, thr_b, off_b,
+                                       z)
+    check(self.lib.wb2_ens_threshold_metrics(
+        self.handle, _P(x), _P(t), F32, int(nmember), int(member_stride),
+        int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
+        *targs, C.byref(w), int(bool(skipna)), _P(out)))
+    del keep
+
+  def gaussian_metrics(self, mean: int, std: int, t: int, off_mean: np.ndarray,
+                       off_std: np.ndarray, off_t: np.ndarray, nthreshold: int,
+                       thr_a: Optional[int], off_a: Optional[np.ndarray],
+                       thr_b: Optional[int], off_b: Optional[np.ndarray],
+                       z: Optional[np.ndarray], weights: 'WeightSpec',
+                       skipna: bool, out: int):
+    w = weights.as_struct()
+    targs, keep = self._threshold_args(nthreshold, thr_a, off_a, thr_b, off_b,
+                                       z)
+    check(self.lib.wb2_gaussian_metrics(
+        self.handle, _P(mean), _P(std), _P(t), F32, int(off_mean.size),
+        _as_ptr(off_mean, C.c_int64), _as_ptr(off_std, C.c_int64),
+        _as_ptr(off_t, C.c_int64), *targs, C.byref(w), int(bool(skipna)),
+        _P(out)))
+    del keep
 
   # -- K5 ---------------------------------------------------------------------
   def regrid_conservative(self, src: int, dst: int, nfield: int,

@@ -660,3 +660,133 @@ def run_ens_maps(ctx: _lib.Context, x_op: Operand, t_op: Operand,
   finally:
     for p in staged:
       ctx.free(p)
+
+
+# ---- K7: threshold / Gaussian metrics -----------------------------------------
+THR_NOUT = 8
+
+
+def _threshold_tables(spec, dims, shape, base, staged, ctx):
+  """Device addressing of a threshold spec over the broadcast outer grid.
+  spec: ('field', [op per threshold]) or ('gaussian', mean_op, std_op, [z]).
+  Returns (nq, ops_on_device, builder) where builder(base) -> kernel args."""
+  if spec[0] == 'field':
+    seen: dict = {}  # thresholds that share a climatology array share its upload
+
+    def stage(op):
+      if op.on_device:
+        return op
+      key = id(op.data)
+      if key not in seen:
+        seen[key] = _to_device_operand(ctx, op, staged).addr
+      out = dataclasses.replace(op, addr=seen[key], on_device=True)
+      if hasattr(op, 'gather_terms'):
+        out.gather_terms = op.gather_terms
+      return out
+
+    ops = [stage(op) for op in spec[1]]
+    return len(ops), ops, lambda b: (
+        b, np.ascontiguousarray(np.concatenate([
+            offset_table(op, dims, shape) + (op.addr - b) // 4
+            for op in ops])), None, None, None)
+  m_op = _to_device_operand(ctx, spec[1], staged)
+  s_op = _to_device_operand(ctx, spec[2], staged)
+  z = np.asarray(spec[3], dtype=np.float64)
+  return z.size, [m_op, s_op], lambda b: (
+      b, offset_table(m_op, dims, shape) + (m_op.addr - b) // 4, b,
+      offset_table(s_op, dims, shape) + (s_op.addr - b) // 4, z)
+
+
+def _check_same_grid(first: Operand, others: Sequence[Operand]):
+  for op in others:
+    if (op.layout != first.layout or op.row_stride != first.row_stride or
+        op.nrow != first.nrow or op.ncol != first.ncol):
+      raise ValueError('operands must share layout, grid and row stride '
+                       f'({op.layout}, {op.nrow}x{op.ncol}, {op.row_stride}) vs '
+                       f'({first.layout}, {first.nrow}x{first.ncol}, '
+                       f'{first.row_stride})')
+    if op.dtype != np.float32:
+      raise ValueError('threshold / Gaussian kernels take float32 operands')
+
+
+def run_ens_threshold_metrics(ctx: _lib.Context, x_op: Operand, t_op: Operand,
+                              ens_dim: str, spec, latitude, longitude,
+                              regions: Sequence, skipna: bool,
+                              cell_cache=None):
+  """Runs K7 (ensemble entry) for one variable.  Returns (stats, dims, M):
+  stats has shape outer_shape + (nq, len(regions), 8)."""
+  staged: list = []
+  try:
+    if ens_dim in t_op.outer_dims:
+      raise ValueError(f'truth must not have the {ens_dim!r} dimension')
+    x_op = _to_device_operand(ctx, x_op, staged)
+    t_op = _to_device_operand(ctx, t_op, staged)
+    x_op, m, st = split_member_dim(x_op, ens_dim)
+    dims, shape = broadcast_dims(x_op, t_op)
+    nq, thr_ops, build = _threshold_tables(spec, dims, shape, 0, staged, ctx)
+    _check_same_grid(x_op, [t_op] + thr_ops)
+    base = min(op.addr for op in [x_op, t_op] + thr_ops)
+    off_x = offset_table(x_op, dims, shape) + (x_op.addr - base) // 4
+    off_t = offset_table(t_op, dims, shape) + (t_op.addr - base) // 4
+    thr_a, off_a, thr_b, off_b, z = build(base)
+    nfield = off_x.size
+    nreg = len(regions)
+    groups = build_weights(ctx, np.asarray(latitude), np.asarray(longitude),
+                           regions, x_op.layout, x_op.row_stride, cell_cache)
+    res = np.empty((nfield, nq, nreg, THR_NOUT), dtype=np.float64)
+    for ids, wspec in groups:
+      out_dev = ctx.malloc(nfield * nq * len(ids) * THR_NOUT * 8)
+      try:
+        ctx.ens_threshold_metrics(base, base, m, st, off_x, off_t, nq, thr_a,
+                                  off_a, thr_b, off_b, z, wspec, skipna,
+                                  out_dev)
+        res[:, :, ids, :] = ctx.from_device(
+            out_dev, (nfield, nq, len(ids), THR_NOUT), np.float64)
+      finally:
+        ctx.free(out_dev)
+    return res.reshape(shape + (nq, nreg, THR_NOUT)), dims, m
+  finally:
+    for p in staged:
+      ctx.free(p)
+
+
+def run_gaussian_metrics(ctx: _lib.Context, m_op: Operand, s_op: Operand,
+                         t_op: Operand, spec, latitude, longitude,
+                         regions: Sequence, skipna: bool, cell_cache=None):
+  """Runs K7 (Gaussian entry) for one variable; spec None -> CRPS / variance.
+  Returns (stats, dims): stats has shape outer_shape + (max(nq, 1), R, 8)."""
+  staged: list = []
+  try:
+    m_op = _to_device_operand(ctx, m_op, staged)
+    s_op = _to_device_operand(ctx, s_op, staged)
+    t_op = _to_device_operand(ctx, t_op, staged)
+    dims, shape = broadcast_dims(m_op, s_op, t_op)
+    if spec is not None:
+      nq, thr_ops, build = _threshold_tables(spec, dims, shape, 0, staged, ctx)
+    else:
+      nq, thr_ops, build = 0, [], lambda b: (None, None, None, None, None)
+    _check_same_grid(m_op, [s_op, t_op] + thr_ops)
+    base = min(op.addr for op in [m_op, s_op, t_op] + thr_ops)
+    off_m = offset_table(m_op, dims, shape) + (m_op.addr - base) // 4
+    off_s = offset_table(s_op, dims, shape) + (s_op.addr - base) // 4
+    off_t = offset_table(t_op, dims, shape) + (t_op.addr - base) // 4
+    thr_a, off_a, thr_b, off_b, z = build(base)
+    nfield = off_m.size
+    nreg = len(regions)
+    nq_out = max(nq, 1)
+    groups = build_weights(ctx, np.asarray(latitude), np.asarray(longitude),
+                           regions, m_op.layout, m_op.row_stride, cell_cache)
+    res = np.empty((nfield, nq_out, nreg, THR_NOUT), dtype=np.float64)
+    for ids, wspec in groups:
+      out_dev = ctx.malloc(nfield * nq_out * len(ids) * THR_NOUT * 8)
+      try:
+        ctx.gaussian_metrics(base, base, base, off_m, off_s, off_t, nq, thr_a,
+                             off_a, thr_b, off_b, z, wspec, skipna, out_dev)
+        res[:, :, ids, :] = ctx.from_device(
+            out_dev, (nfield, nq_out, len(ids), THR_NOUT), np.float64)
+      finally:
+        ctx.free(out_dev)
+    return res.reshape(shape + (nq_out, nreg, THR_NOUT)), dims
+  finally:
+    for p in staged:
+      ctx.free(p)

@@ -554,3 +554,10 @@ from weatherbench2_b200._ensemble import (  # noqa: E402  pylint: disable=wrong-
     EnsembleStddevSqrtBeforeTimeAvg, EnsembleVariance, SpatialCRPS,
     SpatialCRPSSkill, SpatialCRPSSpread, SpatialEnsembleMeanMSE,
     SpatialEnsembleVariance, DebiasedSpatialEnsembleMeanMSE, _get_n_ensemble)
+# Gaussian-forecast and threshold metrics live in _thresholded.py.
+from weatherbench2_b200._thresholded import (  # noqa: E402  pylint: disable=wrong-import-position
+    DebiasedEnsembleBrierScore, EnsembleBrierScore, EnsembleIgnoranceScore,
+    EnsembleRPS, GaussianBrierScore, GaussianCRPS, GaussianIgnoranceScore,
+    GaussianRPS, GaussianVariance, SpatialDebiasedEnsembleBrierScore,
+    SpatialEnsembleBrierScore, SpatialEnsembleIgnoranceScore,
+    SpatialEnsembleRPS, ThresholdMetric)
