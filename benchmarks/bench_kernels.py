@@ -262,14 +262,72 @@ def bench_maps(args):
     del x, t
 
 
+def bench_threshold(args):
+  """K7: ensemble Brier / debiased / ignorance / RPS for 4 Gaussian-quantile
+  thresholds from one pass, and the Gaussian-forecast entry."""
+  torch, _lib, ctx = setup()
+  from weatherbench2_b200 import _spatial as sp
+  lat = np.linspace(-90, 90, NLAT)
+  lon = np.arange(NLON) * 0.25
+  (_, spec), = sp.build_weights(ctx, lat, lon, [None], 'lat_lon', NLON)
+  slab = NLAT * NLON
+  nfield = args.fields
+  z = np.array([-1.2816, -0.5244, 0.5244, 1.2816])
+  for m in args.members:
+    x = torch.randn((m, nfield, NLAT, NLON), device='cuda',
+                    dtype=torch.float32)
+    t = torch.randn((nfield, NLAT, NLON), device='cuda', dtype=torch.float32)
+    cm = torch.zeros((NLAT, NLON), device='cuda', dtype=torch.float32)
+    cs = torch.ones((NLAT, NLON), device='cuda', dtype=torch.float32)
+    base = min(p.data_ptr() for p in (x, t, cm, cs))
+    rel = lambda p: (p.data_ptr() - base) // 4
+    off_x = np.arange(nfield, dtype=np.int64) * slab + rel(x)
+    off_t = np.arange(nfield, dtype=np.int64) * slab + rel(t)
+    off_a = np.zeros(nfield, dtype=np.int64) + rel(cm)
+    off_b = np.zeros(nfield, dtype=np.int64) + rel(cs)
+    out = torch.zeros((nfield, 4, 1, 8), device='cuda', dtype=torch.float64)
+    fn = lambda: ctx.ens_threshold_metrics(
+        base, base, m, nfield * slab, off_x, off_t, 4, base, off_a, base,
+        off_b, z, spec, False, out.data_ptr())
+    ms = timeit(fn, args.steps)
+    pts = nfield * slab
+    report(f'ens_threshold_metrics M={m} 4 thresholds', ms,
+           pts * (4 * m + 4), pts, 'grid_points',
+           {'note': 'climatology mean/std slab (8 MB) is L2-resident'})
+    del x
+  f = torch.randn((nfield * 10, NLAT, NLON), device='cuda',
+                  dtype=torch.float32)
+  s = torch.rand((nfield * 10, NLAT, NLON), device='cuda',
+                 dtype=torch.float32) + 0.5
+  t = torch.randn((nfield * 10, NLAT, NLON), device='cuda',
+                  dtype=torch.float32)
+  nf = nfield * 10
+  base = min(p.data_ptr() for p in (f, s, t, cm, cs))
+  rel = lambda p: (p.data_ptr() - base) // 4
+  offs = [np.arange(nf, dtype=np.int64) * slab + rel(p) for p in (f, s, t)]
+  off_a = np.zeros(nf, dtype=np.int64) + rel(cm)
+  off_b = np.zeros(nf, dtype=np.int64) + rel(cs)
+  out = torch.zeros((nf, 4, 1, 8), device='cuda', dtype=torch.float64)
+  for nq in (0, 4):
+    fn = lambda: ctx.gaussian_metrics(
+        base, base, base, offs[0], offs[1], offs[2], nq, base if nq else None,
+        off_a if nq else None, base if nq else None, off_b if nq else None,
+        z[:nq] if nq else None, spec, False, out.data_ptr())
+    ms = timeit(fn, args.steps)
+    cells = nf * slab
+    report(f'gaussian_metrics nthreshold={nq}', ms, cells * 12, cells,
+           'grid_cells')
+
+
 if __name__ == '__main__':
   ap = argparse.ArgumentParser()
   ap.add_argument('--kernel', required=True,
                   choices=['ens', 'energy', 'det', 'regrid', 'spectrum',
-                           'maps'])
+                           'maps', 'threshold'])
   ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--fields', type=int, default=39)
   ap.add_argument('--members', type=int, nargs='+', default=[50])
   a = ap.parse_args()
   {'ens': bench_ens, 'energy': bench_energy, 'det': bench_det, 'regrid': bench_regrid,
-   'spectrum': bench_spectrum, 'maps': bench_maps}[a.kernel](a)
+   'spectrum': bench_spectrum, 'maps': bench_maps,
+   'threshold': bench_threshold}[a.kernel](a)

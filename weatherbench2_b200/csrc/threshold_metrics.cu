@@ -105,7 +105,7 @@ struct SegAcc {
 };
 
 template <int TQ, bool SKIPNA, bool GAUSS>
-__global__ void __launch_bounds__(kThrThreads, 3) threshold_kernel(const ThrParams p) {
+__global__ void __launch_bounds__(kThrThreads, 4) threshold_kernel(const ThrParams p) {
   constexpr int NV = TQ * kThrStats;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* red = reinterpret_cast<double*>(smem_raw);  // [warps][32][2 * NV]
@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(kThrThreads, 3) threshold_kernel(const ThrPara
   const bool zero_skip = p.zero_skip != 0;
   const float nanv = __int_as_float(0x7fc00000);
 
-  double accd[2 * NV];
+  // float64 accumulators live in shared memory (touched once per row segment):
+  // keeping 2 * NV doubles in registers would cost occupancy, and this kernel
+  // needs many member loads in flight.
+  double* accd = red + (warp * 32 + lane) * 2 * NV;
 #pragma unroll
   for (int i = 0; i < 2 * NV; ++i) accd[i] = 0.0;
 
@@ -156,30 +159,41 @@ __global__ void __launch_bounds__(kThrThreads, 3) threshold_kernel(const ThrPara
         float val[NV];
         if (GAUSS) {
           // ---- Gaussian forecast N(mean, std) ----------------------------------
-          const double mean = double(ldg_stream(px + cell));
-          const double sd = double(ldg_stream(ps + cell));
+          // The reference evaluates scipy.stats.norm in float64.  erfc / exp in
+          // float64 would make this kernel FP64-bound (measured 0.02-0.09 of
+          // the HBM roofline), so the transcendental part runs in float32 --
+          // always on the tail where erfcf keeps full RELATIVE accuracy -- and
+          // only the reference's `1 - cdf` rounding step is replayed in
+          // float64 (it decides when the ignorance score saturates to inf).
+          const float mean = ldg_stream(px + cell);
+          const float sd = ldg_stream(ps + cell);
           if (p.nq == 0) {
             // GaussianCRPS (metrics.py:889-899) and GaussianVariance (:918-922)
-            const double zn = (mean - double(t)) / sd;
-            const double cdf = 0.5 * erfc(-zn * 0.70710678118654752440);
-            const double pdf = 0.39894228040143267794 * exp(-0.5 * zn * zn);
-            val[0] = float(sd * (zn * (2.0 * cdf - 1.0) + 2.0 * pdf - 0.56418958354775628695));
-            val[1] = float(sd * sd);
+            const float zn = (mean - t) / sd;
+            const float az = fabsf(zn);
+            // |z| (2 Phi(|z|) - 1) = |z| (1 - erfc(|z| / sqrt 2)): even in z
+            const float tail = erfcf(az * 0.70710678f);
+            const float pdf = 0.39894228f * expf(-0.5f * zn * zn);
+            val[0] = sd * (az * (1.f - tail) + 2.f * pdf - 0.56418958f);
+            val[1] = sd * sd;
 #pragma unroll
             for (int i = 2; i < NV; ++i) val[i] = 0.f;
           } else {
 #pragma unroll
             for (int q = 0; q < TQ; ++q) {
-              const double zn = (thr[q] - mean) / sd;  // metrics.py:972, 1040, 1112
-              const double cdf = 0.5 * erfc(-zn * 0.70710678118654752440);
+              // metrics.py:972, 1040, 1112
+              const float zn = float(thr[q] - double(mean)) / sd;
+              const float tail = 0.5f * erfcf(fabsf(zn) * 0.70710678f);  // min(cdf, 1 - cdf)
+              // cdf as the reference holds it (float64), then its `1 - cdf`
+              const double cdf = zn > 0.f ? 1.0 - double(tail) : double(tail);
+              const double pe = 1.0 - cdf;  // exceedance probability
               const bool t_gt = t > lo[q];  // truth > threshold (NaN -> false)
               const bool t_lt = t < hi[q];
-              const double pe = 1.0 - cdf;  // exceedance probability
               const double db = pe - (t_gt ? 1.0 : 0.0);
               const double dr = cdf - (t_lt ? 1.0 : 0.0);
               val[q * kThrStats + 0] = float(db * db);                      // :980
               val[q * kThrStats + 1] = 0.f;
-              val[q * kThrStats + 2] = float(-(t_gt ? log(1.0 - cdf) : log(cdf)));  // :1044-1048
+              val[q * kThrStats + 2] = -logf(float(t_gt ? pe : cdf));       // :1044-1048
               val[q * kThrStats + 3] = float(dr * dr);                      // :1118
             }
           }
@@ -190,14 +204,32 @@ __global__ void __launch_bounds__(kThrThreads, 3) threshold_kernel(const ThrPara
           for (int q = 0; q < TQ; ++q) { c_gt[q] = 0.f; c_lt[q] = 0.f; }
           float nvalid = 0.f;
           const float* src = px + cell;
-#pragma unroll 8
-          for (int m = 0; m < M; ++m) {
-            const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
-            nvalid += (xm == xm) ? 1.f : 0.f;
+          // A float64 threshold that is not a float32 number has lo < hi
+          // (adjacent floats), and then  #{x < hi} = #valid - #{x > lo}: one
+          // comparison per (member, threshold) instead of two.
+          bool strict = true;
 #pragma unroll
-            for (int q = 0; q < TQ; ++q) {
-              c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
-              c_lt[q] += (xm < hi[q]) ? 1.f : 0.f;
+          for (int q = 0; q < TQ; ++q) strict = strict && (lo[q] < hi[q] || p.q0 + q >= p.nq);
+          if (__all_sync(__activemask(), strict)) {
+#pragma unroll 10
+            for (int m = 0; m < M; ++m) {
+              const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
+              nvalid += (xm == xm) ? 1.f : 0.f;
+#pragma unroll
+              for (int q = 0; q < TQ; ++q) c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < TQ; ++q) c_lt[q] = nvalid - c_gt[q];
+          } else {
+#pragma unroll 10
+            for (int m = 0; m < M; ++m) {
+              const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
+              nvalid += (xm == xm) ? 1.f : 0.f;
+#pragma unroll
+              for (int q = 0; q < TQ; ++q) {
+                c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
+                c_lt[q] += (xm < hi[q]) ? 1.f : 0.f;
+              }
             }
           }
           const float fm = float(M);
@@ -245,8 +277,6 @@ __global__ void __launch_bounds__(kThrThreads, 3) threshold_kernel(const ThrPara
     }
   }
 
-#pragma unroll
-  for (int i = 0; i < 2 * NV; ++i) red[(warp * 32 + lane) * 2 * NV + i] = accd[i];
   __syncthreads();
   // partial layout: [field][blk][q][r][sums(4), weight sums(4)]
   double* out = p.partial + (field * p.nblk + blk) * int64_t(p.nq > 0 ? p.nq : 1) * R * kThrOut;
