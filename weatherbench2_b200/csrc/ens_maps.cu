@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kEnsMapThreads, 3) ens_maps_kernel(const EnsMa
     }
     const float t = ldg_stream(p.t + p.off_t[j * p.ngroup + g] + cell);
     float pt[kEnsStats];
-    ens_point<MP, SKIPNA, EXACT>(v, t, M, pt);
+    ens_point<MP, SKIPNA, EXACT, kTwinSortOk<MP, SKIPNA, EXACT>>(v, t, M, pt);
     float val[kMapStats];
 #pragma unroll
     for (int i = 0; i < kEnsStats; ++i) val[i] = pt[i];

@@ -48,7 +48,7 @@ struct EnsParams {
   int32_t nblk;
 };
 
-template <int MP, bool SKIPNA, bool EXACT, int OCC>
+template <int MP, bool SKIPNA, bool EXACT, int OCC, bool TWIN = false>
 __global__ void __launch_bounds__(kEnsThreads, OCC) ens_metrics_kernel(const EnsParams p) {
   constexpr int NCNT = SKIPNA ? kEnsStats : 1;
   constexpr int NS = kEnsStats + NCNT;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kEnsThreads, OCC) ens_metrics_kernel(const Ens
           if (zero_skip && wc == 0.f) continue;  // metrics.py:160
         }
         float val[kEnsStats];
-        ens_point<MP, SKIPNA, EXACT>(v, t, M, val);
+        ens_point<MP, SKIPNA, EXACT, TWIN>(v, t, M, val);
 #pragma unroll
         for (int i = 0; i < kEnsStats; ++i) {
           if (SKIPNA) {
@@ -171,6 +171,16 @@ static int launch_ens(wb2_ctx* ctx, const EnsParams& p, int64_t nfield, bool ski
   // resident CTAs per SM the register allocation targets (tuning knob)
   const char* occ_env = getenv("WB2_ENS_OCC");
   const int occ = occ_env ? atoi(occ_env) : (skipna ? 4 : 5);
+  // full even ensembles without NaN handling sort with the packed (FADD2)
+  // network; WB2_ENS_SORT=exact keeps the pure min / max network
+  if constexpr (kTwinSortOk<MP, false, true>) {
+    const char* sort_env = getenv("WB2_ENS_SORT");
+    if (exact && !skipna && !(sort_env && strcmp(sort_env, "exact") == 0)) {
+      if (occ >= 6) return go(ens_metrics_kernel<MP, false, true, 6, true>);
+      if (occ == 5) return go(ens_metrics_kernel<MP, false, true, 5, true>);
+      return go(ens_metrics_kernel<MP, false, true, 4, true>);
+    }
+  }
   if (occ >= 6) {
     if (skipna) return exact ? go(ens_metrics_kernel<MP, true, true, 6>)
                              : go(ens_metrics_kernel<MP, true, false, 6>);

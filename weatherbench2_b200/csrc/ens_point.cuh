@@ -13,17 +13,47 @@ namespace wb2 {
     v[a] = lo_;                           \
     v[b] = hi_;                           \
   }
+// Twin compare-exchange on two aligned register pairs (v[a], v[a+1]) and
+// (v[b], v[b+1]): the minima still cost one FMNMX each (ALU pipe, one warp
+// instruction per 2 cycles per SM sub-partition), but the maxima come from
+// hi = (a + b) - lo as two packed FADD2 on the FMA pipe, which halves the ALU
+// work of those comparators.  (a + b) - lo is not exact: it is only used on
+// mean-removed members, where the rounding error is relative to the ensemble
+// spread (see ens_point below and DESIGN.md, K2).
+__device__ __forceinline__ void ce2_packed(float& a0, float& a1, float& b0, float& b1) {
+  const float l0 = fminf(a0, b0);
+  const float l1 = fminf(a1, b1);
+  unsigned long long pa, pb, pl, ps, ph;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pa) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pb) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pl) : "f"(l0), "f"(l1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ps) : "l"(pa), "l"(pb));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(ph) : "l"(ps), "l"(pl));
+  a0 = l0;
+  a1 = l1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(ph));
+}
+#define CE2(a, b) ce2_packed(v[a], v[(a) + 1], v[b], v[(b) + 1]);
 #include "sort_networks.inc"
 #undef CE
+#undef CE2
 
 constexpr int kEnsStats = 5;
+
+// The packed network applies to full (unpadded), even-sized ensembles without
+// NaN handling: padding is +inf and inf + inf - inf is NaN.
+template <int MP, bool SKIPNA, bool EXACT>
+constexpr bool kTwinSortOk = EXACT && !SKIPNA && MP >= 8 && MP % 2 == 0;
 
 // Point-wise statistics of one grid point.  x[m] for m >= M is padding.
 //   [0] skill_pt  = mean_m |t - x_m|                          (metrics.py:824)
 //   [1] spread_pt = 2 * mean_m((2 r_m - M - 1) x_m) / (M - 1) (metrics.py:805-813)
 //   [2] (t - xbar)^2          [3] var_m(x, ddof=1)     [4] [2] - [3] / M
-template <int MP, bool SKIPNA, bool EXACT>
+// TWIN: sort the mean-removed members with the packed network (the spread sum
+// is invariant to a common shift because its coefficients add up to zero).
+template <int MP, bool SKIPNA, bool EXACT, bool TWIN = false>
 __device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float (&val)[kEnsStats]) {
+  static_assert(!TWIN || kTwinSortOk<MP, SKIPNA, EXACT>, "packed sort needs a full even ensemble");
   const float nanf_ = __int_as_float(0x7fc00000);
   const float inf_ = __int_as_float(0x7f800000);
   float sumx = 0.f, suma = 0.f;
@@ -54,6 +84,7 @@ __device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float 
       } else {
         ss += dx * dx;
       }
+      if (TWIN) v[m] = dx;
     }
   }
   float var;
@@ -76,7 +107,8 @@ __device__ __forceinline__ void ens_point(float (&v)[MP], float t, int M, float 
     if (!EXACT && m >= M) v[m] = inf_;          // padding sorts last
     else if (SKIPNA && !(v[m] == v[m])) v[m] = inf_;  // NaN sorts last (np.argsort)
   }
-  SortNet<MP>::run(v);
+  if constexpr (TWIN) SortNetTwin<MP>::run(v);
+  else SortNet<MP>::run(v);
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MP; ++i) {

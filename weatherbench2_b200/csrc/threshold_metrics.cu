@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThrThreads, 4) threshold_kernel(const ThrPara
 #pragma unroll
           for (int q = 0; q < TQ; ++q) strict = strict && (lo[q] < hi[q] || p.q0 + q >= p.nq);
           if (__all_sync(__activemask(), strict)) {
-#pragma unroll 10
+#pragma unroll 25
             for (int m = 0; m < M; ++m) {
               const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
               nvalid += (xm == xm) ? 1.f : 0.f;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kThrThreads, 4) threshold_kernel(const ThrPara
 #pragma unroll
             for (int q = 0; q < TQ; ++q) c_lt[q] = nvalid - c_gt[q];
           } else {
-#pragma unroll 10
+#pragma unroll 25
             for (int m = 0; m < M; ++m) {
               const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
               nvalid += (xm == xm) ? 1.f : 0.f;
