@@ -245,6 +245,23 @@ int wb2_ens_threshold_metrics(wb2_ctx* ctx, const void* x, const void* t,
                               const double* z, const wb2_weights* w, int skipna,
                               double* out);
 
+/* Map-output variant: SpatialEnsembleBrierScore (metrics.py:1615-1637),
+ * SpatialDebiasedEnsembleBrierScore (:1701-1710), SpatialEnsembleIgnoranceScore
+ * (:1768-1790), SpatialEnsembleRPS (:1868-1891) and the time mean of
+ * EnsembleMetric.compute (:598-607): fields grouped like wb2_det_maps
+ * (off_* host [nout * ngroup], field thresholds [nthreshold][nout * ngroup]).
+ *   stat  0 brier | 1 debiased brier | 2 ignorance | 3 rps part
+ *   out   device [nthreshold][nout][nrow][ncol] float32                          */
+int wb2_ens_threshold_maps(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                           int32_t nmember, int64_t member_stride, int64_t nout,
+                           int32_t ngroup, const int64_t* off_x,
+                           const int64_t* off_t, int32_t nthreshold,
+                           const void* thr_a, const int64_t* off_a,
+                           const void* thr_b, const int64_t* off_b,
+                           const double* z, int32_t nrow, int32_t ncol,
+                           int64_t row_stride, int32_t stat, int skipna,
+                           float* out);
+
 /* wb2_gaussian_metrics replaces GaussianCRPS / GaussianVariance
  * (metrics.py:849-937) when nthreshold == 0:
  *         out [nfield][1][nregion][8]: [0] sum W*crps [1] sum W*std^2, [4],[5] weights

@@ -369,10 +369,58 @@ def test_threshold_compute_matches_kernel_selection():
     thresholds.QuantileThreshold(climatology=clim, quantile=0.7).compute(tds)
 
 
-def test_spatial_threshold_variants_fail_loudly():
+@pytest.mark.parametrize('ensemble_size,skipna', [(3, False), (10, True)])
+def test_spatial_threshold_maps_match_oracle(ensemble_size, skipna):
+  """SpatialEnsembleBrierScore & co. (metrics.py:1615-1637, 1701-1710,
+  1768-1790, 1868-1891): per-time maps and the fused time mean."""
   from weatherbench2_b200 import metrics, thresholds
-  truth, forecast, clim, *_ = _random_case(3, False)
-  thr = thresholds.GaussianQuantileThreshold(climatology=clim, quantile=0.5)
-  with pytest.raises(NotImplementedError):
-    metrics.SpatialEnsembleBrierScore([thr]).compute_chunk(_ds(**forecast),
-                                                           _ds(**truth))
+  truth, forecast, clim, mean, std, sdims = _random_case(ensemble_size, skipna)
+  quantiles = [0.2, 0.5, 0.8, 0.9, 0.97]
+  thrs = [thresholds.GaussianQuantileThreshold(climatology=clim, quantile=q)
+          for q in quantiles]
+  fds, tds = _ds(**forecast), _ds(**truth)
+  fd, f = forecast['vars']['geopotential']
+  tdm, t = truth['vars']['geopotential']
+  ax = fd.index('realization')
+  od = tuple(d for d in fd if d != 'realization')
+  want = {k: [] for k in ('brier', 'debiased', 'ignorance', 'rps')}
+  for thr, thr_dims in _threshold_arrays(truth, mean, std, sdims, quantiles):
+    ta, _, d1 = orc.align(t, tdm, np.take(f, 0, axis=ax), od)
+    tha, _, d2 = orc.align(thr, thr_dims, np.take(f, 0, axis=ax), od)
+    ta = np.transpose(ta, [d1.index(d) for d in od])
+    tha = np.transpose(tha, [d2.index(d) for d in od])
+    want['brier'].append(orc.ens_brier_pointwise(f, ta, tha, ax, False,
+                                                 skipna))
+    want['debiased'].append(orc.ens_brier_pointwise(f, ta, tha, ax, True,
+                                                    skipna))
+    want['ignorance'].append(orc.ens_ignorance_pointwise(f, ta, tha, ax,
+                                                         skipna))
+    want['rps'].append(orc.ens_rps_part_pointwise(f, ta, tha, ax, skipna))
+  classes = {'brier': metrics.SpatialEnsembleBrierScore,
+             'debiased': metrics.SpatialDebiasedEnsembleBrierScore,
+             'ignorance': metrics.SpatialEnsembleIgnoranceScore,
+             'rps': metrics.SpatialEnsembleRPS}
+
+  def compare(got, exp, exp_dims):
+    a, b, _ = orc.align(np.asarray(got.values), got.dims, exp, exp_dims)
+    finite = np.isfinite(b)
+    np.testing.assert_array_equal(np.isfinite(a), finite)
+    np.testing.assert_allclose(a[finite], b[finite], rtol=RTOL, atol=1e-6)
+    np.testing.assert_array_equal(a[~finite], b[~finite])
+
+  for key, cls in classes.items():
+    got = cls(thrs).compute_chunk(fds, tds, skipna=skipna)['geopotential']
+    if key == 'rps':
+      exp, ed = sum(want[key]), od
+    else:
+      exp, ed = np.stack(want[key]), ('quantile',) + od
+      assert got.dims[0] == 'quantile'
+    compare(got, exp, ed)
+    # time mean fused into the kernel
+    res = cls(thrs).compute(fds, tds, skipna=skipna)
+    assert res.attrs['ensemble_size'] == ensemble_size
+    mean_exp, md = orc.time_mean(exp, ed, skipna=skipna, avg_dim='time')
+    if key == 'ignorance' and not np.isfinite(mean_exp).all():
+      # inf - inf never happens (scores are >= 0) but inf means stay inf
+      pass
+    compare(res['geopotential'], mean_exp, md)

@@ -107,6 +107,10 @@ PROTOTYPES = {
         _P, _P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int64, _I64P, _I64P,
         C.c_int32, _P, _I64P, _P, _I64P, C.POINTER(C.c_double),
         C.POINTER(Weights), C.c_int, _P]),
+    'wb2_ens_threshold_maps': (C.c_int, [
+        _P, _P, _P, C.c_int, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _I64P,
+        _I64P, C.c_int32, _P, _I64P, _P, _I64P, C.POINTER(C.c_double),
+        C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int, _P]),
     'wb2_gaussian_metrics': (C.c_int, [
         _P, _P, _P, _P, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_int32,
         _P, _I64P, _P, _I64P, C.POINTER(C.c_double), C.POINTER(Weights),
@@ -311,6 +315,23 @@ class Context:
         self.handle, _P(x), _P(t), F32, int(nmember), int(member_stride),
         int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
         *targs, C.byref(w), int(bool(skipna)), _P(out)))
+    del keep
+
+  def ens_threshold_maps(self, x: int, t: int, nmember: int,
+                         member_stride: int, nout: int, ngroup: int,
+                         off_x: np.ndarray, off_t: np.ndarray, nthreshold: int,
+                         thr_a: int, off_a: np.ndarray, thr_b: Optional[int],
+                         off_b: Optional[np.ndarray], z: Optional[np.ndarray],
+                         nrow: int, ncol: int, row_stride: int, stat: int,
+                         skipna: bool, out: int):
+    assert off_x.size == nout * ngroup and off_t.size == nout * ngroup
+    targs, keep = self._threshold_args(nthreshold, thr_a, off_a, thr_b, off_b,
+                                       z)
+    check(self.lib.wb2_ens_threshold_maps(
+        self.handle, _P(x), _P(t), F32, int(nmember), int(member_stride),
+        int(nout), int(ngroup), _as_ptr(off_x, C.c_int64),
+        _as_ptr(off_t, C.c_int64), *targs, int(nrow), int(ncol),
+        int(row_stride), int(stat), int(bool(skipna)), _P(out)))
     del keep
 
   def gaussian_metrics(self, mean: int, std: int, t: int, off_mean: np.ndarray,

@@ -790,3 +790,50 @@ def run_gaussian_metrics(ctx: _lib.Context, m_op: Operand, s_op: Operand,
   finally:
     for p in staged:
       ctx.free(p)
+
+
+def run_ens_threshold_maps(ctx: _lib.Context, x_op: Operand, t_op: Operand,
+                           ens_dim: str, spec, stat: int,
+                           reduce_dim: Optional[str], skipna: bool):
+  """Runs the map-output form of K7 for one variable.  Returns (maps, dims,
+  M): maps[nq, ...outer (without reduce_dim)..., nrow, ncol] float32."""
+  staged: list = []
+  try:
+    if ens_dim in t_op.outer_dims:
+      raise ValueError(f'truth must not have the {ens_dim!r} dimension')
+    was_dev = x_op.on_device
+    x_op = _to_device_operand(ctx, x_op, staged)
+    t_op = _to_device_operand(ctx, t_op, staged)
+    x_op, m, st = split_member_dim(x_op, ens_dim)
+    dims, shape = broadcast_dims(x_op, t_op)
+    if reduce_dim is not None and reduce_dim in dims:
+      i = dims.index(reduce_dim)
+      ngroup = shape[i]
+      out_dims = dims[:i] + dims[i + 1:]
+      out_shape = shape[:i] + shape[i + 1:]
+      dims, shape = out_dims + (reduce_dim,), out_shape + (ngroup,)
+    else:
+      ngroup, out_dims, out_shape = 1, dims, shape
+    nq, thr_ops, build = _threshold_tables(spec, dims, shape, 0, staged, ctx)
+    _check_same_grid(x_op, [t_op] + thr_ops)
+    base = min(op.addr for op in [x_op, t_op] + thr_ops)
+    off_x = offset_table(x_op, dims, shape) + (x_op.addr - base) // 4
+    off_t = offset_table(t_op, dims, shape) + (t_op.addr - base) // 4
+    thr_a, off_a, thr_b, off_b, z = build(base)
+    nout = off_x.size // ngroup
+    out_full = (nq,) + tuple(out_shape) + (x_op.nrow, x_op.ncol)
+    tensor, ptr = _alloc_maps(ctx, x_op if was_dev else t_op, out_full,
+                              np.float32)
+    try:
+      ctx.ens_threshold_maps(base, base, m, st, nout, ngroup, off_x, off_t, nq,
+                             thr_a, off_a, thr_b, off_b, z, x_op.nrow,
+                             x_op.ncol, x_op.row_stride, stat, skipna, ptr)
+    except Exception:
+      if tensor is None:
+        ctx.free(ptr)
+      raise
+    maps = _fetch_maps(ctx, tensor, ptr, out_full, np.float32)
+    return maps, tuple(out_dims) + _map_dims(x_op), m
+  finally:
+    for p in staged:
+      ctx.free(p)

@@ -297,52 +297,83 @@ class EnsembleRPS(_EnsembleThresholdMetric):
     return id(self)
 
 
-def _spatial_threshold_not_built(name):
-  raise NotImplementedError(
-      f'{name}: the map-output threshold metrics are not built yet (next: the '
-      'K6e map kernel with the K7 point-wise scores).  There is deliberately '
-      'no NumPy fallback.')
+@dataclasses.dataclass
+class _SpatialEnsembleThresholdMetric(_EnsembleThresholdMetric):
+  """Map-output threshold metrics: `wb2_ens_threshold_maps` gives the per-time
+  score maps (`compute_chunk`) or, in `compute`, their time mean in the same
+  pass.  `region` is ignored like in the reference (spatial_agg=False)."""
+
+  def _maps(self, forecast, truth, reduce_dim, skipna):
+    forecast, truth, native = m._prep(forecast, truth)  # pylint: disable=protected-access
+    ens._get_n_ensemble(forecast, self.ensemble_dim)  # pylint: disable=protected-access
+    ctx = m._context()  # pylint: disable=protected-access
+    thresholds = list(self.thresholds)
+    out = xl.Dataset(attrs=self._attrs())
+    for name in m._common_vars(forecast, truth):  # pylint: disable=protected-access
+      f_da, t_da = forecast[name], truth[name]
+      if LAT not in f_da.dims or LON not in f_da.dims:
+        continue
+      f_da, t_da = xl.align_inner(f_da, t_da)
+      x_op = sp.prepare_operand(f_da, None, np.float32)
+      t_op = sp.prepare_operand(t_da, x_op.layout, np.float32)
+      spec = _threshold_spec(thresholds, truth, name, t_da, x_op.layout)
+      maps, dims, _ = sp.run_ens_threshold_maps(
+          ctx, x_op, t_op, self.ensemble_dim, spec, self._SLOT, reduce_dim,
+          skipna)
+      coords = m._map_coords(dims, f_da, t_da)  # pylint: disable=protected-access
+      coords.pop(self.ensemble_dim, None)
+      if self._SUM:  # metrics.py:1891 `.sum("quantile")`
+        out[name] = xl.DataArray(maps.sum(0), dims, coords, name)
+      else:
+        coords['quantile'] = _quantile_coords(thresholds)
+        out[name] = xl.DataArray(maps, ('quantile',) + tuple(dims), coords,
+                                 name)
+    return m._finish(out, native)  # pylint: disable=protected-access
+
+  def compute_chunk(self, forecast, truth, region=None, skipna=False):
+    del region
+    return self._maps(forecast, truth, None, skipna)
+
+  def compute(self, forecast, truth, region=None, skipna=False):
+    del region
+    fc = xl.from_xarray(forecast)
+    result = self._maps(forecast, truth, m._avg_dim(fc), skipna)  # pylint: disable=protected-access
+    return result.assign_attrs(ensemble_size=fc.sizes[self.ensemble_dim])
 
 
 @dataclasses.dataclass
-class SpatialEnsembleBrierScore(_EnsembleThresholdMetric):
-  """metrics.py:1615-1637 -- not built yet."""
+class SpatialEnsembleBrierScore(_SpatialEnsembleThresholdMetric):
+  """Spatial map of the ensemble Brier score (metrics.py:1615-1637)."""
+  _SLOT = _BRIER
 
   def __hash__(self):
     return id(self)
 
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_threshold_not_built('SpatialEnsembleBrierScore')
-
 
 @dataclasses.dataclass
-class SpatialDebiasedEnsembleBrierScore(_EnsembleThresholdMetric):
-  """metrics.py:1701-1710 -- not built yet."""
+class SpatialDebiasedEnsembleBrierScore(_SpatialEnsembleThresholdMetric):
+  """Spatial map of the debiased ensemble Brier score (metrics.py:1701-1710)."""
+  _SLOT = _DEBIASED
 
   def __hash__(self):
     return id(self)
 
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_threshold_not_built('SpatialDebiasedEnsembleBrierScore')
-
 
 @dataclasses.dataclass
-class SpatialEnsembleIgnoranceScore(_EnsembleThresholdMetric):
-  """metrics.py:1768-1790 -- not built yet."""
+class SpatialEnsembleIgnoranceScore(_SpatialEnsembleThresholdMetric):
+  """Spatial map of the ensemble ignorance score (metrics.py:1768-1790)."""
+  _SLOT = _IGNORANCE
 
   def __hash__(self):
     return id(self)
 
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_threshold_not_built('SpatialEnsembleIgnoranceScore')
-
 
 @dataclasses.dataclass
-class SpatialEnsembleRPS(_EnsembleThresholdMetric):
-  """metrics.py:1868-1891 -- not built yet."""
+class SpatialEnsembleRPS(_SpatialEnsembleThresholdMetric):
+  """Spatial map of the ensemble RPS, summed over thresholds
+  (metrics.py:1868-1891)."""
+  _SLOT = _RPS
+  _SUM = True
 
   def __hash__(self):
     return id(self)
-
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    _spatial_threshold_not_built('SpatialEnsembleRPS')

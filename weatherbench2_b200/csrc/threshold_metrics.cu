@@ -104,6 +104,74 @@ struct SegAcc {
   }
 };
 
+// Point-wise ensemble scores for the TQ thresholds of a pass: counts over the
+// streamed members, then Brier / debiased Brier / ignorance / RPS part.
+template <int TQ, bool SKIPNA>
+__device__ __forceinline__ void ens_threshold_point(const float* __restrict__ src,
+                                                    int64_t member_stride, int M, float t,
+                                                    const float (&lo)[TQ], const float (&hi)[TQ],
+                                                    int nq_left, float (&val)[TQ * kThrStats]) {
+  const float nanv = __int_as_float(0x7fc00000);
+  // ---- ensemble: counts over the members ----------------------------------
+  float c_gt[TQ], c_lt[TQ];
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) { c_gt[q] = 0.f; c_lt[q] = 0.f; }
+  float nvalid = 0.f;
+    // A float64 threshold that is not a float32 number has lo < hi
+  // (adjacent floats), and then  #{x < hi} = #valid - #{x > lo}: one
+  // comparison per (member, threshold) instead of two.
+  bool strict = true;
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) strict = strict && (lo[q] < hi[q] || q >= nq_left);
+  if (__all_sync(__activemask(), strict)) {
+#pragma unroll 25
+    for (int m = 0; m < M; ++m) {
+      const float xm = ldg_stream(src + int64_t(m) * member_stride);
+      nvalid += (xm == xm) ? 1.f : 0.f;
+#pragma unroll
+      for (int q = 0; q < TQ; ++q) c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) c_lt[q] = nvalid - c_gt[q];
+  } else {
+#pragma unroll 25
+    for (int m = 0; m < M; ++m) {
+      const float xm = ldg_stream(src + int64_t(m) * member_stride);
+      nvalid += (xm == xm) ? 1.f : 0.f;
+#pragma unroll
+      for (int q = 0; q < TQ; ++q) {
+        c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
+        c_lt[q] += (xm < hi[q]) ? 1.f : 0.f;
+      }
+    }
+  }
+  const float fm = float(M);
+  const bool t_nan = !(t == t);
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) {
+    // Brier (metrics.py:1523-1560): NaN-aware probabilities
+    const float nv = SKIPNA ? nvalid : fm;
+    float pf = c_gt[q] / nv;  // 0 / 0 -> NaN like nanmean of nothing
+    if (!SKIPNA && nvalid < fm) pf = nanv;
+    const float tp = t_nan ? nanv : (t > lo[q] ? 1.f : 0.f);
+    const float d = pf - tp;
+    const float brier = d * d;
+    // ddof = 1 variance of the 0 / 1 member probabilities (:545-565)
+    const float q1 = 1.f - pf;
+    float var = (c_gt[q] * q1 * q1 + (nv - c_gt[q]) * pf * pf) / (nv - 1.f);
+    if (SKIPNA && !(nvalid > 1.f)) var = nanv;
+    // ignorance (:1713-1729) and RPS part (:1793-1803): plain 0 / 1
+    // indicators, a NaN member counts as "not above" / "not below"
+    const bool t_gt = t > lo[q];
+    const float pi = t_gt ? c_gt[q] / fm : (fm - c_gt[q]) / fm;
+    const float dr = c_lt[q] / fm - (t < hi[q] ? 1.f : 0.f);
+    val[q * kThrStats + 0] = brier;
+    val[q * kThrStats + 1] = brier - var / fm;
+    val[q * kThrStats + 2] = -logf(pi);
+    val[q * kThrStats + 3] = dr * dr;
+  }
+}
+
 template <int TQ, bool SKIPNA, bool GAUSS>
 __global__ void __launch_bounds__(kThrThreads, 4) threshold_kernel(const ThrParams p) {
   constexpr int NV = TQ * kThrStats;
@@ -198,65 +266,8 @@ __global__ void __launch_bounds__(kThrThreads, 4) threshold_kernel(const ThrPara
             }
           }
         } else {
-          // ---- ensemble: counts over the members ----------------------------------
-          float c_gt[TQ], c_lt[TQ];
-#pragma unroll
-          for (int q = 0; q < TQ; ++q) { c_gt[q] = 0.f; c_lt[q] = 0.f; }
-          float nvalid = 0.f;
-          const float* src = px + cell;
-          // A float64 threshold that is not a float32 number has lo < hi
-          // (adjacent floats), and then  #{x < hi} = #valid - #{x > lo}: one
-          // comparison per (member, threshold) instead of two.
-          bool strict = true;
-#pragma unroll
-          for (int q = 0; q < TQ; ++q) strict = strict && (lo[q] < hi[q] || p.q0 + q >= p.nq);
-          if (__all_sync(__activemask(), strict)) {
-#pragma unroll 25
-            for (int m = 0; m < M; ++m) {
-              const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
-              nvalid += (xm == xm) ? 1.f : 0.f;
-#pragma unroll
-              for (int q = 0; q < TQ; ++q) c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < TQ; ++q) c_lt[q] = nvalid - c_gt[q];
-          } else {
-#pragma unroll 25
-            for (int m = 0; m < M; ++m) {
-              const float xm = ldg_stream(src + int64_t(m) * p.member_stride);
-              nvalid += (xm == xm) ? 1.f : 0.f;
-#pragma unroll
-              for (int q = 0; q < TQ; ++q) {
-                c_gt[q] += (xm > lo[q]) ? 1.f : 0.f;
-                c_lt[q] += (xm < hi[q]) ? 1.f : 0.f;
-              }
-            }
-          }
-          const float fm = float(M);
-          const bool t_nan = !(t == t);
-#pragma unroll
-          for (int q = 0; q < TQ; ++q) {
-            // Brier (metrics.py:1523-1560): NaN-aware probabilities
-            const float nv = SKIPNA ? nvalid : fm;
-            float pf = c_gt[q] / nv;  // 0 / 0 -> NaN like nanmean of nothing
-            if (!SKIPNA && nvalid < fm) pf = nanv;
-            const float tp = t_nan ? nanv : (t > lo[q] ? 1.f : 0.f);
-            const float d = pf - tp;
-            const float brier = d * d;
-            // ddof = 1 variance of the 0 / 1 member probabilities (:545-565)
-            const float q1 = 1.f - pf;
-            float var = (c_gt[q] * q1 * q1 + (nv - c_gt[q]) * pf * pf) / (nv - 1.f);
-            if (SKIPNA && !(nvalid > 1.f)) var = nanv;
-            // ignorance (:1713-1729) and RPS part (:1793-1803): plain 0 / 1
-            // indicators, a NaN member counts as "not above" / "not below"
-            const bool t_gt = t > lo[q];
-            const float pi = t_gt ? c_gt[q] / fm : (fm - c_gt[q]) / fm;
-            const float dr = c_lt[q] / fm - (t < hi[q] ? 1.f : 0.f);
-            val[q * kThrStats + 0] = brier;
-            val[q * kThrStats + 1] = brier - var / fm;
-            val[q * kThrStats + 2] = -logf(pi);
-            val[q * kThrStats + 3] = dr * dr;
-          }
+          ens_threshold_point<TQ, SKIPNA>(px + cell, p.member_stride, M, t, lo, hi, p.nq - p.q0,
+                                          val);
         }
         acc.add(val, wc);
       }
@@ -458,4 +469,141 @@ extern "C" int wb2_gaussian_metrics(wb2_ctx* ctx, const void* mean, const void* 
                         static_cast<const float*>(thr_a), static_cast<const float*>(thr_b), z,
                         nthreshold, 1, 0, nfield, off_mean, off_std, off_t, off_a, off_b, w,
                         skipna, out);
+}
+
+// ---- map output (SpatialEnsembleBrierScore & co.) -------------------------------
+// One thread per grid cell of one output map; walks the ngroup (time) slabs that
+// average into it, like K6e.  One statistic per launch, TQ thresholds per pass.
+namespace wb2 {
+
+struct ThrMapExtra {
+  float* out;  // [nq][nout][nrow][ncol]
+  int64_t nout, cells_per_map;
+  int32_t ngroup, stat, bpm;
+};
+
+template <int TQ, bool SKIPNA>
+__global__ void __launch_bounds__(kThrThreads, 4)
+    threshold_maps_kernel(const ThrParams p, const ThrMapExtra e) {
+  const int64_t j = blockIdx.x / e.bpm;
+  const int64_t ci = int64_t(blockIdx.x % e.bpm) * kThrThreads + threadIdx.x;
+  if (ci >= e.cells_per_map) return;
+  const int row = static_cast<int>(ci / p.ncol);
+  const int col = static_cast<int>(ci % p.ncol);
+  const int64_t cell = int64_t(row) * p.row_stride + col;
+  double acc[TQ];
+  int cnt[TQ];
+  float last[TQ];
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) { acc[q] = 0.0; cnt[q] = 0; last[q] = 0.f; }
+  for (int g = 0; g < e.ngroup; ++g) {
+    const int64_t field = j * e.ngroup + g;
+    const float t = ldg_stream(p.t + p.off_t[field] + cell);
+    float lo[TQ], hi[TQ];
+    double thr[TQ];
+    load_thresholds<TQ>(p, field, cell, lo, hi, thr);
+    float val[TQ * kThrStats];
+    ens_threshold_point<TQ, SKIPNA>(p.x + p.off_x[field] + cell, p.member_stride, p.nmember, t, lo,
+                                    hi, p.nq - p.q0, val);
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      const float* vq = val + q * kThrStats;
+      const float v = e.stat == 0 ? vq[0] : (e.stat == 1 ? vq[1] : (e.stat == 2 ? vq[2] : vq[3]));
+      last[q] = v;
+      if (SKIPNA) {
+        if (v == v) { acc[q] += double(v); ++cnt[q]; }
+      } else {
+        acc[q] += double(v);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) {
+    if (p.q0 + q >= p.nq) continue;
+    float r;
+    if (e.ngroup == 1) r = last[q];
+    else if (SKIPNA) r = cnt[q] > 0 ? float(acc[q] / double(cnt[q])) : __int_as_float(0x7fc00000);
+    else r = float(acc[q] / double(e.ngroup));
+    e.out[(int64_t(p.q0 + q) * e.nout + j) * e.cells_per_map + ci] = r;
+  }
+}
+
+template <int TQ>
+static int launch_threshold_maps(wb2_ctx* ctx, const ThrParams& p, const ThrMapExtra& e,
+                                 bool skipna) {
+  const dim3 grid(static_cast<unsigned>(e.nout * e.bpm));
+  if (skipna) threshold_maps_kernel<TQ, true><<<grid, kThrThreads, 0, ctx->stream>>>(p, e);
+  else threshold_maps_kernel<TQ, false><<<grid, kThrThreads, 0, ctx->stream>>>(p, e);
+  WB2_CUDA_TRY(cudaGetLastError());
+  return WB2_OK;
+}
+
+}  // namespace wb2
+
+extern "C" int wb2_ens_threshold_maps(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                                      int32_t nmember, int64_t member_stride, int64_t nout,
+                                      int32_t ngroup, const int64_t* off_x, const int64_t* off_t,
+                                      int32_t nthreshold, const void* thr_a, const int64_t* off_a,
+                                      const void* thr_b, const int64_t* off_b, const double* z,
+                                      int32_t nrow, int32_t ncol, int64_t row_stride, int32_t stat,
+                                      int skipna, float* out) {
+  WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
+  WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_threshold_maps: only WB2_F32 inputs are supported");
+  WB2_REQUIRE(nthreshold >= 1 && nthreshold <= 4096, "nthreshold out of range");
+  WB2_REQUIRE(nmember >= 1 && nmember <= 65536, "nmember out of range");
+  WB2_REQUIRE(stat >= 0 && stat < kThrStats, "stat must be 0..3 (brier, debiased, ignorance, rps)");
+  WB2_REQUIRE(nrow > 0 && ncol > 0 && row_stride >= ncol, "bad grid: nrow=%d ncol=%d", nrow, ncol);
+  WB2_REQUIRE(nout >= 0 && ngroup >= 1, "nout must be >= 0 and ngroup >= 1");
+  if (nout == 0) return WB2_OK;
+  WB2_REQUIRE(x && t && off_x && off_t && out && thr_a && off_a,
+              "x/t/out/thresholds and their offset tables must not be NULL");
+  if (thr_b) WB2_REQUIRE(off_b && z, "Gaussian-quantile thresholds need off_b and z");
+  DeviceGuard guard(ctx->device);
+  const int64_t nfield = nout * ngroup;
+  const bool gq = thr_b != nullptr;
+  Packer pk(ctx);
+  const size_t o_x = pk.add(off_x, nfield * sizeof(int64_t));
+  const size_t o_t = pk.add(off_t, nfield * sizeof(int64_t));
+  const size_t o_a = pk.add(off_a, size_t(gq ? 1 : nthreshold) * nfield * sizeof(int64_t));
+  const size_t o_b = gq ? pk.add(off_b, nfield * sizeof(int64_t)) : 0;
+  const size_t o_z = gq ? pk.add(z, size_t(nthreshold) * sizeof(double)) : 0;
+  WB2_TRY(pk.commit());
+  ThrParams p = {};
+  p.x = static_cast<const float*>(x);
+  p.t = static_cast<const float*>(t);
+  p.thr_a = static_cast<const float*>(thr_a);
+  p.thr_b = static_cast<const float*>(thr_b);
+  p.off_x = pk.dev<int64_t>(o_x);
+  p.off_t = pk.dev<int64_t>(o_t);
+  p.off_a = pk.dev<int64_t>(o_a);
+  p.off_b = gq ? pk.dev<int64_t>(o_b) : nullptr;
+  p.z = gq ? pk.dev<double>(o_z) : nullptr;
+  p.member_stride = member_stride;
+  p.row_stride = row_stride;
+  p.nfield = nfield;
+  p.nmember = nmember;
+  p.nrow = nrow; p.ncol = ncol;
+  p.nq = nthreshold;
+  ThrMapExtra e;
+  e.out = out;
+  e.nout = nout;
+  e.cells_per_map = int64_t(nrow) * ncol;
+  e.ngroup = ngroup;
+  e.stat = stat;
+  e.bpm = static_cast<int32_t>((e.cells_per_map + kThrThreads - 1) / kThrThreads);
+  WB2_REQUIRE(nout * int64_t(e.bpm) < (int64_t(1) << 31), "launch too large");
+  int launches = 0;
+  for (int q0 = 0; q0 < nthreshold;) {
+    const int left = nthreshold - q0;
+    p.q0 = q0;
+    int rc;
+    if (left >= 4) { rc = launch_threshold_maps<4>(ctx, p, e, skipna != 0); q0 += 4; }
+    else if (left >= 2) { rc = launch_threshold_maps<2>(ctx, p, e, skipna != 0); q0 += 2; }
+    else { rc = launch_threshold_maps<1>(ctx, p, e, skipna != 0); q0 += 1; }
+    if (rc != WB2_OK) return rc;
+    ++launches;
+  }
+  ctx->launches += launches;
+  WB2_TRY(pk.release());
+  return WB2_OK;
 }
