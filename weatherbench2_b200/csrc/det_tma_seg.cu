@@ -5,13 +5,16 @@
 // their longitude boxes cut a row into ~15 column segments.  Reducing every
 // (row, segment) across the warp (det_metrics.cu / det_tma.cu) then costs more
 // than the arithmetic.  Here the tile already sits in shared memory (same TMA
-// ring as det_tma.cu), so a lane can own a CONTIGUOUS span of columns: it walks
-// its span once, keeps unweighted f32 partial sums, and whenever the span
-// crosses a segment boundary (or ends) it adds  W_r(row, seg) * partial  into
-// per-region REGISTER accumulators for all regions of the launch -- about two
-// FMAs per cell instead of a 5-step butterfly per statistic per segment.
-// Every 8 tiles (and at field changes) the register accumulators are
-// warp-reduced into float64 shared-memory accumulators; fields are flushed to
+// ring as det_tma.cu), so a lane can own a CONTIGUOUS span of columns -- the
+// SAME span, hence the same column segment, in every row.  The weights
+// factorise as  W_r(row, seg) = row_c[row] * pattern[band(row)][r] * seg_w[seg][r]
+// where the region pattern is constant over a BAND of consecutive rows (the
+// latitude boxes), so the per-row work is only  band_acc += row_c[row] * partial
+// (7 FMAs per span); the regions are applied to the band accumulators when the
+// band changes, every 16 tiles and at field changes, warp-reduced into
+// float64 shared-memory accumulators.  (v2 applied all regions at every span
+// end: 16 x 8 FMAs per 11 cells, as much work as the cells themselves, and 112
+// accumulator registers: 0.53 of the HBM roofline.)  Fields are flushed to
 // per-(CTA, warp, field) float64 partials which det_tma_finalize_kernel adds in
 // a fixed order.  Span width is odd so the scalar LDS of a warp are
 // conflict-free.
@@ -29,7 +32,8 @@ namespace wb2 {
 constexpr int kSegConsumerWarps = 8;
 constexpr int kSegThreads = (kSegConsumerWarps + 1) * 32;
 constexpr int kSegTilesInFlight = kSegConsumerWarps / 2;
-constexpr int kSegDump = 8;  // tiles between register -> shared float64 dumps
+constexpr int kSegDump = 16;  // tiles between band accumulator -> float64 dumps
+constexpr int kSegMaxBands = 128;  // row bands (runs of equal region patterns)
 constexpr int kSegMaxSpans = 64;  // spans per half row (two rounds of 32 lanes)
 
 struct TmaSegParams {
@@ -39,7 +43,10 @@ struct TmaSegParams {
   const int64_t* off_f;
   const int64_t* off_t;
   const int64_t* off_c;
-  const float* row_wf;       // [R][nrow] float32 copy of row_w
+  const float* row_c;        // [nrow] common row factor (max_r |row_w[r][row]|)
+  const int32_t* row_band;   // [nrow] band of the row (runs of equal region patterns)
+  const float* pat;          // [nband][RCH] row_w[r][row] / row_c[row], zero padded
+  int32_t nband;
   const float* seg_wf;       // [nseg][RCH] float32, zero padded
   const int32_t* seg_start;  // [nseg + 1]
   const int4* spans;         // [2][kSegMaxSpans] (first col, end col, segment, -)
@@ -102,6 +109,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   double* dacc = reinterpret_cast<double*>(empty + nstage);  // [warps][RCH][NS]
   float* s_segw = reinterpret_cast<float*>(dacc + kSegConsumerWarps * RCH * NS);  // [nseg][RCH]
   int* s_segstart = reinterpret_cast<int*>(s_segw + size_t(p.nseg) * RCH);       // [nseg + 1]
+  float* s_pat = reinterpret_cast<float*>(s_segstart + p.nseg + 1);               // [nband][RCH]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +123,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   }
   for (int i = threadIdx.x; i < p.nseg * RCH; i += kSegThreads) s_segw[i] = p.seg_wf[i];
   for (int i = threadIdx.x; i <= p.nseg; i += kSegThreads) s_segstart[i] = p.seg_start[i];
+  for (int i = threadIdx.x; i < p.nband * RCH; i += kSegThreads) s_pat[i] = p.pat[i];
   for (int i = threadIdx.x; i < kSegConsumerWarps * RCH * NS; i += kSegThreads) dacc[i] = 0.0;
   __syncthreads();
 
@@ -169,26 +178,48 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   const int nspan = p.nspan[half];
   const int4* spans = p.spans + half * kSegMaxSpans;
 
-  float accr[RCH][NS];
+  // A lane owns the same (at most two) column spans in every row, i.e. fixed
+  // segments.  W_r(row, seg) = row_c[row] * pattern[band(row)][r] * seg_w[seg][r]
+  // with the region pattern constant over a BAND of consecutive rows (the
+  // latitude boxes of the regions), so the per-row work is only
+  // band_acc += row_c[row] * part; the regions are applied when the band
+  // changes, every kSegDump tiles and at field changes.
+  int4 my_span[2];
+  my_span[0] = lane < nspan ? spans[lane] : make_int4(0, 0, 0, 0);
+  my_span[1] = lane + 32 < nspan ? spans[lane + 32] : make_int4(0, 0, 0, 0);
+  float band_acc[2][NS];
 #pragma unroll
-  for (int r = 0; r < RCH; ++r)
+  for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int i = 0; i < NS; ++i) accr[r][i] = 0.f;
+    for (int i = 0; i < NS; ++i) band_acc[k][i] = 0.f;
   double* my_dacc = dacc + warp * RCH * NS;
   int since_dump = 0;
+  int cur_band = -1;
   int64_t cur_field = -1;
 
   auto dump = [&]() {
-    // register accumulators -> float64 shared accumulators of this warp
+    // band accumulators -> regions -> float64 shared accumulators of this warp
+    if (cur_band >= 0 && since_dump > 0) {
+      const float* pat = s_pat + cur_band * RCH;
+      const float* wv0 = s_segw + my_span[0].z * RCH;
+      const float* wv1 = s_segw + my_span[1].z * RCH;
+      for (int r = 0; r < R; ++r) {
+        const float w0 = pat[r] * wv0[r], w1 = pat[r] * wv1[r];
+        const bool use0 = my_span[0].y > my_span[0].x && (w0 != 0.f || !zero_skip);
+        const bool use1 = my_span[1].y > my_span[1].x && (w1 != 0.f || !zero_skip);
 #pragma unroll
-    for (int r = 0; r < RCH; ++r) {
-#pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        const float v = warp_sum(accr[r][i]);
-        if (lane == 0) my_dacc[r * NS + i] += double(v);
-        accr[r][i] = 0.f;
+        for (int i = 0; i < NS; ++i) {
+          float v = use0 ? w0 * band_acc[0][i] : 0.f;
+          if (use1) v = fmaf(w1, band_acc[1][i], v);
+          v = warp_sum(v);
+          if (lane == 0) my_dacc[r * NS + i] += double(v);
+        }
       }
     }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int i = 0; i < NS; ++i) band_acc[k][i] = 0.f;
     since_dump = 0;
     __syncwarp();
   };
@@ -227,11 +258,14 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
       flush_field(cur_field);
       cur_field = field;
     }
-    // float32 row weights of all regions for this row (broadcast loads, issued
-    // before the wait)
-    float u[RCH];
-#pragma unroll
-    for (int r = 0; r < RCH; ++r) u[r] = r < R ? __ldg(p.row_wf + int64_t(r) * p.nrow + row) : 0.f;
+    // common row factor and band of this row (broadcast loads, issued before
+    // the wait)
+    const float crow = __ldg(p.row_c + row);
+    const int band = __ldg(p.row_band + row);
+    if (band != cur_band) {
+      dump();
+      cur_band = band;
+    }
 
     const unsigned char* src = smem + stage_bytes * s;
     const float* sf = reinterpret_cast<const float*>(src);
@@ -239,29 +273,26 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
     const float* sc = reinterpret_cast<const float*>(src + 2 * p.stage_op_bytes);
 
     mbar_wait(&full[s], use & 1);
-    for (int si = lane; si < nspan; si += 32) {
-      const int4 sp = spans[si];  // x = first column, y = end, z = segment
-      float part[NS];
+    if (crow != 0.f || !zero_skip) {  // rows outside every region: metrics.py:160
 #pragma unroll
-      for (int i = 0; i < NS; ++i) part[i] = 0.f;
+      for (int k = 0; k < 2; ++k) {
+        const int4 sp = my_span[k];  // x = first column, y = end, z = segment
+        float part[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) part[i] = 0.f;
 #pragma unroll 4
-      for (int col = sp.x; col < sp.y; ++col)
-        seg_cell<CLIM, SKIPNA>(sf[col], st_[col], CLIM ? sc[col] : 0.f, part);
-      if (!SKIPNA) part[NSUM] = float(sp.y - sp.x);
-      const float* wv = s_segw + sp.z * RCH;
+        for (int col = sp.x; col < sp.y; ++col)
+          seg_cell<CLIM, SKIPNA>(sf[col], st_[col], CLIM ? sc[col] : 0.f, part);
+        if (!SKIPNA) part[NSUM] = float(sp.y - sp.x);
 #pragma unroll
-      for (int r = 0; r < RCH; ++r) {
-        const float w = u[r] * wv[r];
-        if (w != 0.f || !zero_skip) {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) accr[r][i] = fmaf(w, part[i], accr[r][i]);
-        }
+        for (int i = 0; i < NS; ++i) band_acc[k][i] = fmaf(crow, part[i], band_acc[k][i]);
       }
+      ++since_dump;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
 
-    if (++since_dump >= kSegDump) dump();
+    if (since_dump >= kSegDump) dump();
     row += kSegTilesInFlight;
     s += kSegTilesInFlight;
     if (s >= nstage) { s -= nstage; ++use; }
@@ -309,9 +340,44 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
   const int nsum = clim ? 6 : 3;
   const int ns = nsum + (skipna ? (clim ? 4 : 1) : 1);
   const int stage_op_bytes = (w->ncol * 4 + 127) / 128 * 128;
+  // Row bands per region chunk: runs of consecutive rows whose normalised region
+  // pattern row_w[r][row] / max_r |row_w[r][row]| is the same for all regions
+  // of the chunk (the latitude boxes).  Arbitrary per-row patterns (more than
+  // kSegMaxBands runs) take the LDG path.
+  struct ChunkBands {
+    std::vector<float> row_c, pat;
+    std::vector<int32_t> row_band;
+    int nband = 0;
+  };
+  std::vector<ChunkBands> chunks;
+  for (int r0 = 0; r0 < w->nregion; r0 += rch) {
+    const int nreg = std::min(rch, w->nregion - r0);
+    ChunkBands cb;
+    cb.row_c.resize(w->nrow);
+    cb.row_band.resize(w->nrow);
+    std::vector<float> cur(rch, 0.f), prev(rch, 0.f);
+    for (int i = 0; i < w->nrow; ++i) {
+      double cmax = 0.0;
+      for (int r = 0; r < nreg; ++r)
+        cmax = std::max(cmax, std::fabs(w->row_w[size_t(r0 + r) * w->nrow + i]));
+      for (int r = 0; r < rch; ++r)
+        cur[r] = (r < nreg && cmax > 0.0)
+                     ? static_cast<float>(w->row_w[size_t(r0 + r) * w->nrow + i] / cmax)
+                     : 0.f;
+      if (cb.nband == 0 || cur != prev) {
+        if (cb.nband == kSegMaxBands) return 0;
+        cb.pat.insert(cb.pat.end(), cur.begin(), cur.end());
+        ++cb.nband;
+        prev = cur;
+      }
+      cb.row_c[i] = static_cast<float>(cmax);
+      cb.row_band[i] = cb.nband - 1;
+    }
+    chunks.push_back(std::move(cb));
+  }
   const size_t fixed = size_t(kSegConsumerWarps) * rch * ns * sizeof(double) +
                        size_t(w->nseg) * rch * sizeof(float) + size_t(w->nseg + 1) * sizeof(int) +
-                       256;
+                       size_t(kSegMaxBands) * rch * sizeof(float) + 256;
   const size_t budget = 220 * 1024;
   if (fixed >= budget) return 0;
   int nstage = static_cast<int>((budget - fixed) / (size_t(noper) * stage_op_bytes + 16));
@@ -360,13 +426,11 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
   for (int r0 = 0; r0 < w->nregion; r0 += rch) {
     const int nreg = std::min(rch, w->nregion - r0);
     // float32 weights of this region chunk
-    std::vector<float> row_wf(size_t(nreg) * w->nrow), seg_wf(size_t(w->nseg) * rch, 0.f);
-    for (int r = 0; r < nreg; ++r) {
-      for (int i = 0; i < w->nrow; ++i)
-        row_wf[size_t(r) * w->nrow + i] = static_cast<float>(w->row_w[size_t(r0 + r) * w->nrow + i]);
+    const ChunkBands& cb = chunks[r0 / rch];
+    std::vector<float> seg_wf(size_t(w->nseg) * rch, 0.f);
+    for (int r = 0; r < nreg; ++r)
       for (int k = 0; k < w->nseg; ++k)
         seg_wf[size_t(k) * rch + r] = static_cast<float>(w->seg_w[size_t(r0 + r) * w->nseg + k]);
-    }
     const size_t per_field = size_t(nreg) * WB2_DET_NSTAT;
     const size_t part_bytes =
         size_t(ncta) * kSegConsumerWarps * maxslots * per_field * sizeof(double);
@@ -383,7 +447,9 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
       ctx->tma_partial_cap = need;
     }
     Packer pk(ctx);
-    size_t o1 = pk.add(row_wf.data(), row_wf.size() * sizeof(float));
+    size_t o1 = pk.add(cb.row_c.data(), cb.row_c.size() * sizeof(float));
+    size_t o5 = pk.add(cb.row_band.data(), cb.row_band.size() * sizeof(int32_t));
+    size_t o6 = pk.add(cb.pat.data(), cb.pat.size() * sizeof(float));
     size_t o2 = pk.add(seg_wf.data(), seg_wf.size() * sizeof(float));
     size_t o3 = pk.add(w->seg_start, size_t(w->nseg + 1) * sizeof(int32_t));
     size_t o4 = pk.add(h_spans.data(), h_spans.size() * sizeof(int4));
@@ -394,7 +460,8 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
     p.t = static_cast<const float*>(t);
     p.c = static_cast<const float*>(c);
     p.off_f = d_off_f; p.off_t = d_off_t; p.off_c = d_off_c;
-    p.row_wf = pk.dev<float>(o1); p.seg_wf = pk.dev<float>(o2);
+    p.row_c = pk.dev<float>(o1); p.seg_wf = pk.dev<float>(o2);
+    p.row_band = pk.dev<int32_t>(o5); p.pat = pk.dev<float>(o6); p.nband = cb.nband;
     p.seg_start = pk.dev<int32_t>(o3);
     p.spans = pk.dev<int4>(o4);
     p.nspan[0] = h_nspan[0]; p.nspan[1] = h_nspan[1];
