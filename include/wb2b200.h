@@ -304,6 +304,27 @@ int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* dst,
                             int64_t dst_field_stride, const wb2_csr* lon_w,
                             const wb2_csr* lat_w);
 
+/* ---- K8: nearest-neighbour and bilinear regridding -----------------------------
+ * wb2_regrid_gather replaces NearestRegridder.regrid_array
+ * (regridding.py:231-247): dst[k] = src[indices[k]], `indices` host [ntarget]
+ * into the raveled (lon, lat) source slab (BallTree / haversine nearest
+ * neighbours, computed by the binder like regridding.py:212-228).
+ * wb2_regrid_bilinear replaces BilinearRegridder.regrid_array (:256-294): per
+ * target longitude a / latitude c two source taps and the fraction
+ * delta / dx of jnp.interp (host arrays; tap -1 = NaN outside the source);
+ * latitude is interpolated first, then longitude, in float32.
+ * Slabs are (lon, lat) with lat contiguous; strides in elements.               */
+int wb2_regrid_gather(wb2_ctx* ctx, const float* src, float* dst, int64_t nfield,
+                      int64_t src_field_stride, int64_t dst_field_stride,
+                      int32_t nsource, int32_t ntarget, const int32_t* indices);
+int wb2_regrid_bilinear(wb2_ctx* ctx, const float* src, float* dst,
+                        int64_t nfield, int64_t src_field_stride,
+                        int64_t dst_field_stride, int32_t nlon_s, int32_t nlat_s,
+                        int32_t nlon_t, int32_t nlat_t, const int32_t* lon_i0,
+                        const int32_t* lon_i1, const float* lon_t,
+                        const int32_t* lat_i0, const int32_t* lat_i1,
+                        const float* lat_t);
+
 /* ---- K4: zonal energy spectrum ---------------------------------------------
  * Replaces ZonalEnergySpectrum.compute (weatherbench2/derived_variables.py:
  * 592-626): rfft(norm='forward') along longitude, |F_k|^2 * (1 if k==0 else 2),

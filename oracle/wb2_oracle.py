@@ -822,3 +822,52 @@ def ens_rps_part_pointwise(x, t, thr, ax, skipna):
   truth_ecdf = np.where(t < thr, 1.0, 0.0)
   forecast_ecdf = np.where(x < np.expand_dims(thr, ax), 1.0, 0.0)
   return (_mean(forecast_ecdf, ax, skipna) - truth_ecdf) ** 2
+
+
+# ---------------------------------------------------------------------------
+# Nearest-neighbour and bilinear regridding -- regridding.py:212-294.
+# ---------------------------------------------------------------------------
+def nearest_neighbor_indices(source: Grid, target: Grid) -> np.ndarray:
+  """regridding.py:212-228 (same BallTree / haversine query)."""
+  from sklearn import neighbors
+  source_mesh = np.meshgrid(np.deg2rad(source.latitudes),
+                            np.deg2rad(source.longitudes))
+  target_mesh = np.meshgrid(np.deg2rad(target.latitudes),
+                            np.deg2rad(target.longitudes))
+  index_coords = np.stack([x.ravel() for x in source_mesh], axis=-1)
+  query_coords = np.stack([x.ravel() for x in target_mesh], axis=-1)
+  tree = neighbors.BallTree(index_coords, metric="haversine")
+  return tree.query(query_coords, return_distance=False).squeeze(axis=-1)
+
+
+def nearest_regrid(field, source: Grid, target: Grid):
+  """NearestRegridder.regrid_array, regridding.py:231-247; (..., lon, lat)."""
+  field = np.asarray(field)
+  if field.shape[-2:] != source.shape:
+    raise ValueError(f"expected {field.shape=} to match {source.shape=}")
+  idx = nearest_neighbor_indices(source, target)
+  flat = field.reshape(field.shape[:-2] + (-1,))
+  return np.take(flat, idx, axis=-1).reshape(field.shape[:-2] + target.shape)
+
+
+def bilinear_regrid(field, source: Grid, target: Grid):
+  """BilinearRegridder.regrid_array, regridding.py:256-294.  jnp.interp has
+  np.interp's semantics (left / right / period); evaluated here in float64."""
+  field = np.asarray(field, dtype=np.float64)
+  lead = field.shape[:-2]
+  x = field.reshape((-1,) + field.shape[-2:])
+  # latitude (regridding.py:262-274): clamp at the ends iff the source has poles
+  kw = {} if source.includes_poles else dict(left=np.nan, right=np.nan)
+  lat_out = np.empty(x.shape[:2] + (len(target.latitudes),))
+  for n in range(x.shape[0]):
+    for b in range(x.shape[1]):
+      lat_out[n, b] = np.interp(target.latitudes, source.latitudes, x[n, b],
+                                **kw)
+  # longitude (:276-292): periodic wrap-around or NaN outside
+  kw = dict(period=360) if source.periodic else dict(left=np.nan, right=np.nan)
+  out = np.empty((x.shape[0], len(target.longitudes), len(target.latitudes)))
+  for n in range(x.shape[0]):
+    for c in range(lat_out.shape[2]):
+      out[n, :, c] = np.interp(target.longitudes, source.longitudes,
+                               lat_out[n, :, c], **kw)
+  return out.reshape(lead + out.shape[1:])

@@ -596,3 +596,40 @@ def test_debiased_brier_integrates_to_crps():
   skill = np.abs(x - t).mean()
   spread = np.abs(x[0] - x[1]).mean()
   np.testing.assert_allclose(integral, skill - 0.5 * spread, rtol=5e-3)
+
+
+# ---- nearest / bilinear regridders: regridding_test.py:495-591 ----------------
+@pytest.mark.parametrize('periodic,expected', [
+    (True, [[0.5], [1.5], [2.5], [1.5]]), (False, [[0.5], [1.5], [2.5], [np.nan]])])
+def test_bilinear_regridder_longitude_periodicity(periodic, expected):
+  src = orc.Grid(longitudes=np.array([0.0, 90.0, 180.0, 270.0]),
+                 latitudes=np.array([0]), includes_poles=True, periodic=periodic)
+  tgt = orc.Grid(longitudes=np.array([45.0, 135.0, 225.0, 315.0]),
+                 latitudes=np.array([0]), includes_poles=True, periodic=periodic)
+  got = orc.bilinear_regrid(np.array([[0.0], [1.0], [2.0], [3.0]]), src, tgt)
+  np.testing.assert_allclose(got, expected, atol=1e-6)
+
+
+@pytest.mark.parametrize('poles,slat,tlat,vals,expected', [
+    (True, [-90.0, -30.0, 30.0, 90.0], [-60.0, 0.0, 60.0], [0.0, 1.0, 2.0, 3.0],
+     [[0.5, 1.5, 2.5]]),
+    (True, [-60.0, 0.0, 60.0], [-90.0, -30.0, 30.0, 90.0], [0.0, 1.0, 2.0],
+     [[0.0, 0.5, 1.5, 2.0]]),
+    (False, [-60.0, -20.0, 20.0, 60.0], [-70.0, 0.0, 70.0],
+     [0.0, 1.0, 2.0, 3.0], [[np.nan, 1.5, np.nan]])])
+def test_bilinear_regridder_latitude_poles(poles, slat, tlat, vals, expected):
+  src = orc.Grid(longitudes=np.array([0.0]), latitudes=np.array(slat),
+                 includes_poles=poles, periodic=True)
+  tgt = orc.Grid(longitudes=np.array([0.0]), latitudes=np.array(tlat),
+                 includes_poles=poles, periodic=True)
+  got = orc.bilinear_regrid(np.array(vals)[np.newaxis, :], src, tgt)
+  np.testing.assert_allclose(got, expected, atol=1e-6)
+
+
+def test_nearest_regridder_exact():
+  src = orc.Grid(longitudes=np.array([0, 90, 180, 270]),
+                 latitudes=np.array([-30, 0, 30]))
+  tgt = orc.Grid(longitudes=np.array([0, 180]), latitudes=np.array([-30, 0, 30]))
+  field = np.array([[0, 1, 2], [4, 5, 6], [7, 8, 9], [10, 11, 12]])
+  got = orc.nearest_regrid(field, src, tgt)
+  np.testing.assert_allclose(got, [[0, 1, 2], [7, 8, 9]], atol=1e-6)

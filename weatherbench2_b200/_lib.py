@@ -118,6 +118,14 @@ PROTOTYPES = {
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
+    'wb2_regrid_gather': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_int32)]),
+    'wb2_regrid_bilinear': (C.c_int, [
+        _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+        C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+        C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+        C.POINTER(C.c_float)]),
     'wb2_zonal_spectrum': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32,
                                      C.POINTER(C.c_double), _P, C.c_int32,
                                      C.c_int64]),
@@ -358,6 +366,32 @@ class Context:
     check(self.lib.wb2_regrid_conservative(
         self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
         int(dst_stride), C.byref(a), C.byref(b)))
+
+  # -- K8 ---------------------------------------------------------------------
+  def regrid_gather(self, src: int, dst: int, nfield: int, src_stride: int,
+                    dst_stride: int, nsource: int, indices: np.ndarray):
+    idx = np.ascontiguousarray(indices, dtype=np.int32)
+    check(self.lib.wb2_regrid_gather(
+        self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
+        int(dst_stride), int(nsource), int(idx.size),
+        _as_ptr(idx, C.c_int32)))
+
+  def regrid_bilinear(self, src: int, dst: int, nfield: int, src_stride: int,
+                      dst_stride: int, source_shape, lon_taps, lat_taps):
+    """lon_taps / lat_taps: (i0, i1, t) arrays per target coordinate."""
+    li0, li1, lt = (np.ascontiguousarray(lon_taps[0], np.int32),
+                    np.ascontiguousarray(lon_taps[1], np.int32),
+                    np.ascontiguousarray(lon_taps[2], np.float32))
+    ai0, ai1, at = (np.ascontiguousarray(lat_taps[0], np.int32),
+                    np.ascontiguousarray(lat_taps[1], np.int32),
+                    np.ascontiguousarray(lat_taps[2], np.float32))
+    check(self.lib.wb2_regrid_bilinear(
+        self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
+        int(dst_stride), int(source_shape[0]), int(source_shape[1]),
+        int(li0.size), int(ai0.size), _as_ptr(li0, C.c_int32),
+        _as_ptr(li1, C.c_int32), _as_ptr(lt, C.c_float),
+        _as_ptr(ai0, C.c_int32), _as_ptr(ai1, C.c_int32),
+        _as_ptr(at, C.c_float)))
 
   # -- K4 ---------------------------------------------------------------------
   def zonal_spectrum(self, x: int, nfield: int, nrow: int, ncol: int,

@@ -158,9 +158,43 @@ class Regridder:
   source: Grid
   target: Grid
 
-  def regrid_array(self, field):
-    """Regrid an array with dimensions (..., lon, lat)."""
+  def regrid_device(self, ctx: _lib.Context, src_ptr: int, dst_ptr: int,
+                    nfield: int, src_stride: Optional[int] = None,
+                    dst_stride: Optional[int] = None):
+    """Raw device-pointer entry: `nfield` float32 slabs (lon, lat) -> slabs."""
     raise NotImplementedError
+
+  def regrid_array(self, field):
+    """(..., lon, lat) -> (..., lon_target, lat_target), float32 like the
+    reference (JAX default).  NumPy in -> NumPy out; CUDA tensor in -> out."""
+    ctx = _lib.default_context()
+    is_torch = xl._is_torch(field)  # pylint: disable=protected-access
+    shape = tuple(field.shape)
+    if shape[-2:] != self.source.shape:
+      raise ValueError(f'expected trailing dims {self.source.shape}, got '
+                       f'{shape[-2:]}')
+    batch = shape[:-2]
+    nfield = int(np.prod(batch)) if batch else 1
+    tshape = batch + self.target.shape
+    if is_torch and field.is_cuda:
+      import torch  # pylint: disable=import-outside-toplevel
+      x = field.to(torch.float32).contiguous()
+      out = torch.empty(tshape, device=field.device, dtype=torch.float32)
+      stream = torch.cuda.current_stream(field.device)
+      stream.synchronize()
+      self.regrid_device(ctx, x.data_ptr(), out.data_ptr(), nfield)
+      ctx.synchronize()
+      return out
+    x = np.ascontiguousarray(np.asarray(field), dtype=np.float32)
+    nt = self.target.shape[0] * self.target.shape[1]
+    src = ctx.to_device(x)
+    dst = ctx.malloc(max(1, nfield * nt * 4))
+    try:
+      self.regrid_device(ctx, src, dst, nfield)
+      return ctx.from_device(dst, tshape, np.float32)
+    finally:
+      ctx.free(src)
+      ctx.free(dst)
 
   def regrid_dataset(self, dataset):
     """Regrid a Dataset from source to target (regridding.py:193-209)."""
@@ -217,34 +251,7 @@ class ConservativeRegridder(Regridder):
     ctx.regrid_conservative(src_ptr, dst_ptr, nfield, src_stride or ns,
                             dst_stride or nt, lon_w, lat_w)
 
-  def regrid_array(self, field):
-    """(..., lon, lat) -> (..., lon_target, lat_target), float32 like the
-    reference (JAX default).  NumPy in -> NumPy out; CUDA tensor in -> out."""
-    ctx = _lib.default_context()
-    is_torch = xl._is_torch(field)  # pylint: disable=protected-access
-    shape = tuple(field.shape)
-    if shape[-2:] != self.source.shape:
-      raise ValueError(f'expected trailing dims {self.source.shape}, got '
-                       f'{shape[-2:]}')
-    batch = shape[:-2]
-    nfield = int(np.prod(batch)) if batch else 1
-    tshape = batch + self.target.shape
-    if is_torch and field.is_cuda:
-      import torch  # pylint: disable=import-outside-toplevel
-      x = field.to(torch.float32).contiguous()
-      out = torch.empty(tshape, device=field.device, dtype=torch.float32)
-      stream = torch.cuda.current_stream(field.device)
-      stream.synchronize()
-      self.regrid_device(ctx, x.data_ptr(), out.data_ptr(), nfield)
-      ctx.synchronize()
-      return out
-    x = np.ascontiguousarray(np.asarray(field), dtype=np.float32)
-    nt = self.target.shape[0] * self.target.shape[1]
-    src = ctx.to_device(x)
-    dst = ctx.malloc(max(1, nfield * nt * 4))
-    try:
-      self.regrid_device(ctx, src, dst, nfield)
-      return ctx.from_device(dst, tshape, np.float32)
-    finally:
-      ctx.free(src)
-      ctx.free(dst)
+
+# Nearest / bilinear regridders live in _regrid_interp.py (they need Regridder).
+from weatherbench2_b200._regrid_interp import (  # noqa: E402  pylint: disable=wrong-import-position
+    BilinearRegridder, NearestRegridder, nearest_neighbor_indices)
