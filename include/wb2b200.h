@@ -219,6 +219,25 @@ int wb2_ens_maps(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                  int32_t nrow, int32_t ncol, int64_t row_stride,
                  int32_t stat_mask, int skipna, float* out);
 
+/* ---- K9: SEEPS maps ---------------------------------------------------------------
+ * Replaces SpatialSEEPS.compute_chunk (metrics.py:417-513) and, for ngroup > 1,
+ * the time mean of Metric.compute: dry / light / heavy categories of forecast
+ * and truth precipitation, the 3 x 3 scoring matrix of the cell's
+ * climatological dry fraction p1, NaN where p1 is outside (min_p1, max_p1).
+ * SEEPS (the spatial mean with skipna, :516-528) is wb2_det_metrics on the maps.
+ *   wet          device base of the climatological wet-threshold slabs;
+ *   off_wet_f/t  host [nout * ngroup]: the slab for the forecast's / truth's
+ *                valid time (day-of-year / hour lookup folded into the table)
+ *   p1           device [nrow][ncol] float32 mean dry fraction
+ *   out          device [nout][nrow][ncol] float32                               */
+int wb2_seeps_maps(wb2_ctx* ctx, const float* f, const float* t, const float* wet,
+                   const float* p1, int64_t nout, int32_t ngroup,
+                   const int64_t* off_f, const int64_t* off_t,
+                   const int64_t* off_wet_f, const int64_t* off_wet_t,
+                   int32_t nrow, int32_t ncol, int64_t row_stride,
+                   int64_t wet_row_stride, float dry_threshold, float min_p1,
+                   float max_p1, int skipna, float* out);
+
 /* ---- K7: threshold ("binary event") and Gaussian-forecast metrics -------------
  * wb2_ens_threshold_metrics replaces EnsembleBrierScore /
  * DebiasedEnsembleBrierScore (metrics.py:1523-1710), EnsembleIgnoranceScore

@@ -871,3 +871,35 @@ def bilinear_regrid(field, source: Grid, target: Grid):
       out[n, :, c] = np.interp(target.longitudes, source.longitudes,
                                lat_out[n, :, c], **kw)
   return out.reshape(lead + out.shape[1:])
+
+
+# ---------------------------------------------------------------------------
+# SEEPS -- metrics.py:417-528.
+# ---------------------------------------------------------------------------
+def seeps_pointwise(f, t, wet_f, wet_t, p1, dry_threshold_mm=0.25, min_p1=0.1,
+                    max_p1=0.85):
+  """SpatialSEEPS.compute_chunk on arrays that broadcast against each other:
+  f / t precipitation, wet_f / wet_t the climatological wet threshold at their
+  valid times, p1 the mean dry fraction."""
+  dry_threshold = dry_threshold_mm / 1000.0
+
+  def cats(x, wet):  # metrics.py:446-460
+    dry = x < dry_threshold
+    light = np.logical_and(x > dry_threshold, x < wet)
+    heavy = x >= wet
+    c = np.stack([dry, light, heavy]).astype(int).astype(float)
+    return np.where(np.isnan(x)[None], np.nan, c)
+
+  fc, tc = cats(f, wet_f), cats(t, wet_t)
+  out = fc[:, None] * tc[None, :]  # [forecast_cat, truth_cat, ...]
+  z = np.zeros_like(p1, dtype=np.float64)
+  with np.errstate(divide="ignore", invalid="ignore"):
+    matrix = 0.5 * np.stack([  # metrics.py:482-494
+        np.stack([z, 1 / (1 - p1), 4 / (1 - p1)]),
+        np.stack([1 / p1, z, 3 / (1 - p1)]),
+        np.stack([1 / p1 + 3 / (2 + p1), 3 / (2 + p1), z])])
+  extra = out.ndim - 2 - np.ndim(p1)  # p1 has the trailing (spatial) dims
+  matrix = matrix.reshape(matrix.shape[:2] + (1,) * extra + matrix.shape[2:])
+  result = (out * matrix).sum(axis=(0, 1))  # xr.dot: NaN propagates
+  result = np.where(p1 < max_p1, result, np.nan)  # :503-504
+  return np.where(p1 > min_p1, result, np.nan)

@@ -633,3 +633,15 @@ def test_nearest_regridder_exact():
   field = np.array([[0, 1, 2], [4, 5, 6], [7, 8, 9], [10, 11, 12]])
   got = orc.nearest_regrid(field, src, tgt)
   np.testing.assert_allclose(got, [[0, 1, 2], [7, 8, 9]], atol=1e-6)
+
+
+def test_seeps_known_answers():
+  """metrics_test.py:1392-1440: perfect forecast -> 0; forecast light while the
+  observation is dry -> 0.5 / p1 = 1.25 at p1 = 0.4."""
+  t = np.zeros((3, 4), np.float32)
+  wet = np.ones((3, 4), np.float32)
+  p1 = np.full((3, 4), 0.4, np.float32)
+  np.testing.assert_allclose(orc.seeps_pointwise(t, t, wet, wet, p1), 0,
+                             atol=1e-4)
+  np.testing.assert_allclose(orc.seeps_pointwise(t + 0.5, t, wet, wet, p1),
+                             1.25, atol=1e-4)

@@ -118,6 +118,10 @@ PROTOTYPES = {
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
+    'wb2_seeps_maps': (C.c_int, [
+        _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _I64P, _I64P, _I64P, _I64P,
+        C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float,
+        C.c_float, C.c_int, _P]),
     'wb2_regrid_gather': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_int32, C.c_int32,
                                     C.POINTER(C.c_int32)]),
@@ -366,6 +370,24 @@ class Context:
     check(self.lib.wb2_regrid_conservative(
         self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
         int(dst_stride), C.byref(a), C.byref(b)))
+
+  # -- K9 ---------------------------------------------------------------------
+  def seeps_maps(self, f: int, t: int, wet: int, p1: int, nout: int,
+                 ngroup: int, off_f: np.ndarray, off_t: np.ndarray,
+                 off_wet_f: np.ndarray, off_wet_t: np.ndarray, nrow: int,
+                 ncol: int, row_stride: int, wet_row_stride: int,
+                 dry_threshold: float, min_p1: float, max_p1: float,
+                 skipna: bool, out: int):
+    n = nout * ngroup
+    assert off_f.size == n and off_t.size == n
+    assert off_wet_f.size == n and off_wet_t.size == n
+    check(self.lib.wb2_seeps_maps(
+        self.handle, _P(f), _P(t), _P(wet), _P(p1), int(nout), int(ngroup),
+        _as_ptr(off_f, C.c_int64), _as_ptr(off_t, C.c_int64),
+        _as_ptr(off_wet_f, C.c_int64), _as_ptr(off_wet_t, C.c_int64),
+        int(nrow), int(ncol), int(row_stride), int(wet_row_stride),
+        float(dry_threshold), float(min_p1), float(max_p1),
+        int(bool(skipna)), _P(out)))
 
   # -- K8 ---------------------------------------------------------------------
   def regrid_gather(self, src: int, dst: int, nfield: int, src_stride: int,
