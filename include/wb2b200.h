@@ -238,6 +238,21 @@ int wb2_seeps_maps(wb2_ctx* ctx, const float* f, const float* t, const float* we
                    int64_t wet_row_stride, float dry_threshold, float min_p1,
                    float max_p1, int skipna, float* out);
 
+/* ---- K10: rank histogram ---------------------------------------------------------
+ * Replaces RankHistogram.compute_chunk (metrics.py:1894-2042) and the time mean
+ * of EnsembleMetric.compute: rank of the truth among the members (NaN last),
+ * binned into nbins (nbins divides nmember + 1), one-hot per grid point or,
+ * for ngroup > 1, the mean of the one-hots over the group.  random_ties != 0
+ * places the truth uniformly among members exactly equal to it (the effect of
+ * the reference's tie-breaking noise) using a counter-based hash of `seed`.
+ *   out   device [nout][nrow][ncol][nbins] float32                                */
+int wb2_rank_histogram(wb2_ctx* ctx, const float* x, const float* t,
+                       int32_t nmember, int64_t member_stride, int64_t nout,
+                       int32_t ngroup, const int64_t* off_x, const int64_t* off_t,
+                       int32_t nrow, int32_t ncol, int64_t row_stride,
+                       int32_t nbins, int32_t random_ties, uint64_t seed,
+                       float* out);
+
 /* ---- K7: threshold ("binary event") and Gaussian-forecast metrics -------------
  * wb2_ens_threshold_metrics replaces EnsembleBrierScore /
  * DebiasedEnsembleBrierScore (metrics.py:1523-1710), EnsembleIgnoranceScore

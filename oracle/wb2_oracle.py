@@ -903,3 +903,27 @@ def seeps_pointwise(f, t, wet_f, wet_t, p1, dry_threshold_mm=0.25, min_p1=0.1,
   result = (out * matrix).sum(axis=(0, 1))  # xr.dot: NaN propagates
   result = np.where(p1 < max_p1, result, np.nan)  # :503-504
   return np.where(p1 > min_p1, result, np.nan)
+
+
+# ---------------------------------------------------------------------------
+# RankHistogram -- metrics.py:1894-2042 (without the random tie-breaking noise:
+# truth is prepended to the members and a STABLE argsort keeps it first among
+# equal values; NaN sorts last).
+# ---------------------------------------------------------------------------
+def rank_histogram_one_hot(f, fdims, t, tdims, ens_dim, num_bins=None):
+  fdims = tuple(fdims)
+  ax = fdims.index(ens_dim)
+  m = f.shape[ax]
+  od = tuple(d for d in fdims if d != ens_dim)
+  ta, fa0, d = align(t, tdims, np.take(f, 0, axis=ax), od)
+  ta = np.broadcast_to(np.transpose(ta, [d.index(x) for x in od]),
+                       np.take(f, 0, axis=ax).shape)
+  combined = np.concatenate([np.expand_dims(ta, ax), f], axis=ax)  # :2000-2009
+  order = np.argsort(combined, axis=ax, kind="stable")
+  ranks = np.argmin(order, axis=ax)  # position of element 0 (truth), :2027
+  default_bins = m + 1
+  nb = default_bins if num_bins is None else num_bins
+  if default_bins % nb:
+    raise ValueError(f"Cannot bin data with ensemble_size={m} into {nb} bins")
+  ranks = ranks // (default_bins // nb)  # :1950-1958
+  return np.eye(nb)[ranks], od + ("bins",)

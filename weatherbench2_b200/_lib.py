@@ -118,6 +118,10 @@ PROTOTYPES = {
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
+    'wb2_rank_histogram': (C.c_int, [
+        _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _I64P, _I64P,
+        C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
+        _P]),
     'wb2_seeps_maps': (C.c_int, [
         _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _I64P, _I64P, _I64P, _I64P,
         C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_float, C.c_float,
@@ -370,6 +374,18 @@ class Context:
     check(self.lib.wb2_regrid_conservative(
         self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
         int(dst_stride), C.byref(a), C.byref(b)))
+
+  # -- K10 --------------------------------------------------------------------
+  def rank_histogram(self, x: int, t: int, nmember: int, member_stride: int,
+                     nout: int, ngroup: int, off_x: np.ndarray,
+                     off_t: np.ndarray, nrow: int, ncol: int, row_stride: int,
+                     nbins: int, random_ties: bool, seed: int, out: int):
+    assert off_x.size == nout * ngroup and off_t.size == nout * ngroup
+    check(self.lib.wb2_rank_histogram(
+        self.handle, _P(x), _P(t), int(nmember), int(member_stride),
+        int(nout), int(ngroup), _as_ptr(off_x, C.c_int64),
+        _as_ptr(off_t, C.c_int64), int(nrow), int(ncol), int(row_stride),
+        int(nbins), int(bool(random_ties)), int(seed) & (2**64 - 1), _P(out)))
 
   # -- K9 ---------------------------------------------------------------------
   def seeps_maps(self, f: int, t: int, wet: int, p1: int, nout: int,

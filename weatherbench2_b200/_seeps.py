@@ -138,27 +138,6 @@ class SpatialSEEPS(m.Metric):
     return m._finish(out, native)  # pylint: disable=protected-access
 
 
-class RankHistogram(m.Metric):
-  """Histogram of truth's rank within the ensemble (metrics.py:1894-2042) --
-  NOT built: with `break_ties_randomly` (the default) the reference perturbs
-  every value with NumPy's PCG64 stream, which a GPU kernel cannot reproduce
-  bit for bit; it is the one metric class of the reference without a kernel
-  here.  Fails loudly instead of falling back to NumPy."""
-
-  def __init__(self, ensemble_dim: str = 'realization',
-               num_bins: t.Optional[int] = None,
-               break_ties_randomly: bool = True, seed: t.Optional[int] = None):
-    self.ensemble_dim = ensemble_dim
-    self.num_bins = num_bins
-    self._break_ties_randomly = break_ties_randomly
-    self._seed = seed
-
-  def compute_chunk(self, forecast, truth, region=None, skipna=False):
-    raise NotImplementedError(
-        'RankHistogram is not built (see DESIGN.md, section 8); there is '
-        'deliberately no NumPy fallback.')
-
-
 @dataclasses.dataclass
 class SEEPS(SpatialSEEPS):
   """Spatially averaged SEEPS (metrics.py:516-528): the weighted mean of the
