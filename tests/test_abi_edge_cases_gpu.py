@@ -140,6 +140,43 @@ def test_all_nan_and_zero_weight_regions():
   assert np.isnan(got.values).all()
 
 
+def test_threads_share_the_default_context():
+  """Chunks evaluated from several threads against the process-wide context
+  (Beam DirectRunner style, weatherbench2/evaluation.py:697, 733) give the
+  same results as sequential calls."""
+  import concurrent.futures
+  from weatherbench2_b200 import metrics, regions as R, xarray_lite as xl
+  lat = np.linspace(-90, 90, 19)
+  lon = np.linspace(0, 360, 36, endpoint=False)
+  dims = ('time', 'level', 'latitude', 'longitude')
+  coords = {'time': np.arange(4), 'level': np.arange(3), 'latitude': lat,
+            'longitude': lon}
+  rs = np.random.RandomState(0)
+  chunks = []
+  for _ in range(16):
+    f = rs.normal(size=(4, 3, 19, 36)).astype(np.float32)
+    t = rs.normal(size=(4, 3, 19, 36)).astype(np.float32)
+    x = rs.normal(size=(5, 4, 3, 19, 36)).astype(np.float32)
+    chunks.append((xl.Dataset({'a': (dims, f)}, coords),
+                   xl.Dataset({'a': (dims, t)}, coords),
+                   xl.Dataset({'a': (('realization',) + dims, x)},
+                              dict(coords, realization=np.arange(5)))))
+  region = R.SliceRegion(lat_slice=slice(-30, 60))
+
+  def work(chunk):
+    f, t, x = chunk
+    return (metrics.MSE().compute_chunk(f, t, region=region)['a'].values,
+            metrics.CRPS().compute_chunk(x, t)['a'].values,
+            np.asarray(metrics.SpatialMAE().compute(f, t)['a'].values))
+
+  want = [work(c) for c in chunks]
+  with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+    got = list(pool.map(work, chunks))
+  for g, w in zip(got, want):
+    for a, b in zip(g, w):
+      np.testing.assert_array_equal(a, b)
+
+
 def test_many_fields_and_more_than_32_regions():
   """7 800 fields in one launch (the size of a 10-init chunk at configs[1]) on a
   small grid, and 40 regions (split into launches of <= 32)."""

@@ -172,11 +172,38 @@ def _as_ptr(a: Optional[np.ndarray], ctype):
   return a.ctypes.data_as(C.POINTER(ctype))
 
 
+class _LockedLib:
+  """The library with every call into it serialised by the context's lock.  A
+  wb2_ctx (stream, descriptor slots, scratch) is not re-entrant, ctypes drops
+  the GIL during a call, and the reference's callers may evaluate chunks from
+  several threads (Beam DirectRunner, weatherbench2/evaluation.py:697, 733)
+  against the process-wide default context.  Error strings are thread-local
+  on the C side, so `check()` may read them after the lock is released."""
+
+  def __init__(self, lib, lock):
+    self._lib = lib
+    self._lock = lock
+
+  def __getattr__(self, name):
+    fn = getattr(self._lib, name)
+    lock = self._lock
+
+    def call(*args):
+      with lock:
+        return fn(*args)
+
+    call.__name__ = name
+    setattr(self, name, call)  # cache: __getattr__ only runs on a miss
+    return call
+
+
 class Context:
-  """A wb2_ctx: one CUDA device + stream + descriptor arenas."""
+  """A wb2_ctx: one CUDA device + stream + descriptor arenas.  Safe to share
+  between threads (calls are serialised per context)."""
 
   def __init__(self, device: int = 0):
-    self.lib = load_library()
+    self._lock = threading.RLock()
+    self.lib = _LockedLib(load_library(), self._lock)
     h = _P()
     check(self.lib.wb2_create(int(device), C.byref(h)))
     self.handle = h
