@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1) det_tma_kernel(const TmaParams
 
 __global__ void det_tma_finalize_kernel(const double* __restrict__ partial,
                                         double* __restrict__ out, int64_t ntiles, int ncta,
-                                        int tiles_per_field, int maxslots, int per_field) {
+                                        int tiles_per_field, int maxslots, int per_field,
+                                        int nwarps) {
   const int64_t field = blockIdx.x;
   const int64_t tf0 = field * tiles_per_field, tf1 = tf0 + tiles_per_field;
   const int64_t per = ntiles / ncta, extra = ntiles % ncta;
@@ -257,8 +258,8 @@ __global__ void det_tma_finalize_kernel(const double* __restrict__ partial,
       const int64_t t1 = t0 + per + (b < extra ? 1 : 0);
       if (t1 <= tf0 || t0 >= tf1) continue;
       const int slot = static_cast<int>(field - t0 / tiles_per_field);
-      for (int w = 0; w < kConsumerWarps; ++w)
-        v += partial[((int64_t(b) * kConsumerWarps + w) * maxslots + slot) * per_field + i];
+      for (int w = 0; w < nwarps; ++w)
+        v += partial[((int64_t(b) * nwarps + w) * maxslots + slot) * per_field + i];
     }
     out[field * per_field + i] = v;
   }
@@ -268,9 +269,9 @@ __global__ void det_tma_finalize_kernel(const double* __restrict__ partial,
 // fixed-order finalize without relocatable device code.
 int launch_det_tma_finalize(wb2_ctx* ctx, const double* partial, double* out, int64_t nfield,
                             int64_t ntiles, int ncta, int tiles_per_field, int maxslots,
-                            int per_field) {
+                            int per_field, int nwarps) {
   det_tma_finalize_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
-      partial, out, ntiles, ncta, tiles_per_field, maxslots, per_field);
+      partial, out, ntiles, ncta, tiles_per_field, maxslots, per_field, nwarps);
   WB2_CUDA_TRY(cudaGetLastError());
   return WB2_OK;
 }
@@ -333,7 +334,7 @@ int det_metrics_tma(wb2_ctx* ctx, bool clim, const void* f, const void* t, const
   if (rc != WB2_OK) return rc;
   det_tma_finalize_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
       p.partial, out, p.ntiles, ncta, p.tiles_per_field, p.maxslots,
-      static_cast<int>(per_field));
+      static_cast<int>(per_field), kConsumerWarps);
   WB2_CUDA_TRY(cudaGetLastError());
   ctx->launches += 2;
   return 1;

@@ -29,9 +29,11 @@
 
 namespace wb2 {
 
-constexpr int kSegConsumerWarps = 8;
-constexpr int kSegThreads = (kSegConsumerWarps + 1) * 32;
-constexpr int kSegTilesInFlight = kSegConsumerWarps / 2;
+// Consumer warps per CTA (template parameter CW below): 2 warps share a tile
+// (half a row each), so CW / 2 tiles are consumed at once.  The kernel is
+// latency-bound (dependent LDS -> FMA chains), so more warps help; 16 is the
+// default, WB2_SEG_WARPS=8 selects the smaller shape.
+constexpr int kSegDefaultWarps = 16;
 constexpr int kSegDump = 16;  // tiles between band accumulator -> float64 dumps
 constexpr int kSegMaxBands = 128;  // row bands (runs of equal region patterns)
 constexpr int kSegMaxSpans = 64;  // spans per half row (two rounds of 32 lanes)
@@ -93,8 +95,8 @@ __device__ __forceinline__ void seg_cell(float f, float t, float c, float* part)
   }
 }
 
-template <bool CLIM, bool SKIPNA, int RCH>
-__global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSegParams p) {
+template <bool CLIM, bool SKIPNA, int RCH, int CW>
+__global__ void __launch_bounds__(((CW + 1) * 32), 1) det_tma_seg_kernel(const TmaSegParams p) {
   constexpr int NOPER = CLIM ? 3 : 2;
   constexpr int NSUM = CLIM ? 6 : 3;
   // per-piece values: sums, then counts (skipna) or one cell count (!skipna)
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stage_bytes * nstage);
   uint64_t* empty = full + nstage;
   double* dacc = reinterpret_cast<double*>(empty + nstage);  // [warps][RCH][NS]
-  float* s_segw = reinterpret_cast<float*>(dacc + kSegConsumerWarps * RCH * NS);  // [nseg][RCH]
+  float* s_segw = reinterpret_cast<float*>(dacc + CW * RCH * NS);  // [nseg][RCH]
   int* s_segstart = reinterpret_cast<int*>(s_segw + size_t(p.nseg) * RCH);       // [nseg + 1]
   float* s_pat = reinterpret_cast<float*>(s_segstart + p.nseg + 1);               // [nband][RCH]
 
@@ -121,10 +123,10 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < p.nseg * RCH; i += kSegThreads) s_segw[i] = p.seg_wf[i];
-  for (int i = threadIdx.x; i <= p.nseg; i += kSegThreads) s_segstart[i] = p.seg_start[i];
-  for (int i = threadIdx.x; i < p.nband * RCH; i += kSegThreads) s_pat[i] = p.pat[i];
-  for (int i = threadIdx.x; i < kSegConsumerWarps * RCH * NS; i += kSegThreads) dacc[i] = 0.0;
+  for (int i = threadIdx.x; i < p.nseg * RCH; i += ((CW + 1) * 32)) s_segw[i] = p.seg_wf[i];
+  for (int i = threadIdx.x; i <= p.nseg; i += ((CW + 1) * 32)) s_segstart[i] = p.seg_start[i];
+  for (int i = threadIdx.x; i < p.nband * RCH; i += ((CW + 1) * 32)) s_pat[i] = p.pat[i];
+  for (int i = threadIdx.x; i < CW * RCH * NS; i += ((CW + 1) * 32)) dacc[i] = 0.0;
   __syncthreads();
 
   const int64_t per = p.ntiles / gridDim.x, extra = p.ntiles % gridDim.x;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   const int64_t ncta_tiles = t1 - t0;
   const int64_t first_field = t0 / p.nrow;
 
-  if (warp == kSegConsumerWarps) {
+  if (warp == CW) {
     // ------------------------------ producer --------------------------------
     if (lane == 0) {
       int64_t field = first_field;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
     dump();
     const int slot = static_cast<int>(field - first_field);
     double* out = p.partial +
-                  ((int64_t(blockIdx.x) * kSegConsumerWarps + warp) * p.maxslots + slot) *
+                  ((int64_t(blockIdx.x) * CW + warp) * p.maxslots + slot) *
                       int64_t(R) * WB2_DET_NSTAT;
     for (int idx = lane; idx < R * WB2_DET_NSTAT; idx += 32) {
       const int r = idx / WB2_DET_NSTAT;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
   int row = static_cast<int>(t0 - first_field * p.nrow) + pair;
   int s = pair;
   uint32_t use = 0;
-  for (int64_t j = pair; j < ncta_tiles; j += kSegTilesInFlight) {
+  for (int64_t j = pair; j < ncta_tiles; j += (CW / 2)) {
     while (row >= p.nrow) { row -= p.nrow; ++field; }
     if (field != cur_field) {
       flush_field(cur_field);
@@ -293,8 +295,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
     if (lane == 0) mbar_arrive(&empty[s]);
 
     if (since_dump >= kSegDump) dump();
-    row += kSegTilesInFlight;
-    s += kSegTilesInFlight;
+    row += (CW / 2);
+    s += (CW / 2);
     if (s >= nstage) { s -= nstage; ++use; }
   }
   flush_field(cur_field);
@@ -302,25 +304,25 @@ __global__ void __launch_bounds__(kSegThreads, 1) det_tma_seg_kernel(const TmaSe
 
 int launch_det_tma_finalize(wb2_ctx* ctx, const double* partial, double* out, int64_t nfield,
                             int64_t ntiles, int ncta, int tiles_per_field, int maxslots,
-                            int per_field);
+                            int per_field, int nwarps);
 
 // Returns 1 if the kernel ran, 0 if not eligible, < 0 on error.  Handles the
 // regions [r0, r0 + nreg) of `w`; `out` is the full [nfield][w->nregion][10]
 // array (this launch fills only its regions).
-template <int RCH>
+template <int RCH, int CW>
 static int launch_seg(wb2_ctx* ctx, bool clim, bool skipna, const TmaSegParams& p, int ncta,
                       size_t smem) {
   auto go = [&](auto kernel) -> int {
     WB2_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-    kernel<<<ncta, kSegThreads, smem, ctx->stream>>>(p);
+    kernel<<<ncta, ((CW + 1) * 32), smem, ctx->stream>>>(p);
     WB2_CUDA_TRY(cudaGetLastError());
     return WB2_OK;
   };
-  if (clim) return skipna ? go(det_tma_seg_kernel<true, true, RCH>)
-                          : go(det_tma_seg_kernel<true, false, RCH>);
-  return skipna ? go(det_tma_seg_kernel<false, true, RCH>)
-                : go(det_tma_seg_kernel<false, false, RCH>);
+  if (clim) return skipna ? go(det_tma_seg_kernel<true, true, RCH, CW>)
+                          : go(det_tma_seg_kernel<true, false, RCH, CW>);
+  return skipna ? go(det_tma_seg_kernel<false, true, RCH, CW>)
+                : go(det_tma_seg_kernel<false, false, RCH, CW>);
 }
 
 __global__ void seg_scatter_kernel(const double* __restrict__ tmp, double* __restrict__ out,
@@ -336,6 +338,8 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
                         const int64_t* d_off_c, const wb2_weights* w, int skipna, double* out) {
   const int noper = clim ? 3 : 2;
   if (w->ncol * 4 < 512 || w->ncol % 4 != 0) return 0;
+  const char* cw_env = getenv("WB2_SEG_WARPS");
+  const int CW = (cw_env && atoi(cw_env) == 8) ? 8 : kSegDefaultWarps;
   const int rch = skipna ? 8 : 16;
   const int nsum = clim ? 6 : 3;
   const int ns = nsum + (skipna ? (clim ? 4 : 1) : 1);
@@ -375,15 +379,17 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
     }
     chunks.push_back(std::move(cb));
   }
-  const size_t fixed = size_t(kSegConsumerWarps) * rch * ns * sizeof(double) +
+  const size_t fixed = size_t(CW) * rch * ns * sizeof(double) +
                        size_t(w->nseg) * rch * sizeof(float) + size_t(w->nseg + 1) * sizeof(int) +
                        size_t(kSegMaxBands) * rch * sizeof(float) + 256;
   const size_t budget = 220 * 1024;
   if (fixed >= budget) return 0;
   int nstage = static_cast<int>((budget - fixed) / (size_t(noper) * stage_op_bytes + 16));
-  nstage = nstage / kSegTilesInFlight * kSegTilesInFlight;
   if (nstage > 32) nstage = 32;
-  if (nstage < 2 * kSegTilesInFlight) return 0;
+  // CW / 2 stages are being consumed at any time; the rest is what the TMA
+  // producer keeps in flight (>= 3 rows ~ 52 KB, above the ~44 KB per SM that
+  // saturate HBM)
+  if (nstage < CW / 2 + 3) return 0;
   const size_t smem = size_t(nstage) * noper * stage_op_bytes + 2 * nstage * sizeof(uint64_t) + fixed;
 
   const int64_t ntiles = nfield * w->nrow;
@@ -433,7 +439,7 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
         seg_wf[size_t(k) * rch + r] = static_cast<float>(w->seg_w[size_t(r0 + r) * w->nseg + k]);
     const size_t per_field = size_t(nreg) * WB2_DET_NSTAT;
     const size_t part_bytes =
-        size_t(ncta) * kSegConsumerWarps * maxslots * per_field * sizeof(double);
+        size_t(ncta) * CW * maxslots * per_field * sizeof(double);
     const size_t tmp_bytes = size_t(nfield) * per_field * sizeof(double);
     const size_t need = part_bytes + tmp_bytes;
     if (need > ctx->tma_partial_cap) {
@@ -471,13 +477,17 @@ int det_metrics_tma_seg(wb2_ctx* ctx, bool clim, const void* f, const void* t, c
     p.nregion = nreg; p.nseg = w->nseg; p.zero_skip = w->zero_skip;
     p.nstage = nstage; p.stage_op_bytes = stage_op_bytes; p.maxslots = maxslots;
     WB2_CUDA_TRY(cudaMemsetAsync(p.partial, 0, part_bytes, ctx->stream));
-    int rc = skipna ? launch_seg<8>(ctx, clim, true, p, ncta, smem)
-                    : launch_seg<16>(ctx, clim, false, p, ncta, smem);
+    int rc;
+    if (CW == 16) rc = skipna ? launch_seg<8, 16>(ctx, clim, true, p, ncta, smem)
+                              : launch_seg<16, 16>(ctx, clim, false, p, ncta, smem);
+    else rc = skipna ? launch_seg<8, 8>(ctx, clim, true, p, ncta, smem)
+                     : launch_seg<16, 8>(ctx, clim, false, p, ncta, smem);
     if (rc != WB2_OK) return rc;
     double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->tma_partial) + part_bytes);
     const bool direct = (nreg == w->nregion);
     WB2_TRY(launch_det_tma_finalize(ctx, p.partial, direct ? out : tmp, nfield, ntiles, ncta,
-                                    w->nrow, maxslots, static_cast<int>(per_field)));
+                                    w->nrow, maxslots, static_cast<int>(per_field),
+                                    CW));
     ctx->launches += 2;
     if (!direct) {
       seg_scatter_kernel<<<static_cast<unsigned>(nfield), 128, 0, ctx->stream>>>(
