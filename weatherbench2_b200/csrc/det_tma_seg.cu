@@ -207,16 +207,21 @@ __global__ void __launch_bounds__(((CW + 1) * 32), 1) det_tma_seg_kernel(const T
       const float* wv0 = s_segw + my_span[0].z * RCH;
       const float* wv1 = s_segw + my_span[1].z * RCH;
       for (int r = 0; r < R; ++r) {
+        // a region that does not contain this band gets nothing (warp-uniform
+        // test: most bands touch only a few of the regions)
+        if (zero_skip && pat[r] == 0.f) continue;
         const float w0 = pat[r] * wv0[r], w1 = pat[r] * wv1[r];
         const bool use0 = my_span[0].y > my_span[0].x && (w0 != 0.f || !zero_skip);
         const bool use1 = my_span[1].y > my_span[1].x && (w1 != 0.f || !zero_skip);
+        float mine = 0.f;  // lane i ends up with the total of statistic i
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
           float v = use0 ? w0 * band_acc[0][i] : 0.f;
           if (use1) v = fmaf(w1, band_acc[1][i], v);
           v = warp_sum(v);
-          if (lane == 0) my_dacc[r * NS + i] += double(v);
+          if (lane == i) mine = v;
         }
+        if (lane < NS) my_dacc[r * NS + lane] += double(mine);
       }
     }
 #pragma unroll
