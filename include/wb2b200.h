@@ -238,6 +238,13 @@ int wb2_seeps_maps(wb2_ctx* ctx, const float* f, const float* t, const float* we
                    int64_t wet_row_stride, float dry_threshold, float min_p1,
                    float max_p1, int skipna, float* out);
 
+/* ---- derived variables -------------------------------------------------------------
+ * wb2_wind_speed replaces WindSpeed.compute (derived_variables.py:77-99):
+ * out[i] = sqrt(u[i]^2 + v[i]^2) in float32, bit-identical to NumPy; device
+ * pointers, n elements.                                                          */
+int wb2_wind_speed(wb2_ctx* ctx, const float* u, const float* v, float* out,
+                   int64_t n);
+
 /* ---- K10: rank histogram ---------------------------------------------------------
  * Replaces RankHistogram.compute_chunk (metrics.py:1894-2042) and the time mean
  * of EnsembleMetric.compute: rank of the truth among the members (NaN last),

@@ -118,6 +118,7 @@ PROTOTYPES = {
     'wb2_regrid_conservative': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64,
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
+    'wb2_wind_speed': (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     'wb2_rank_histogram': (C.c_int, [
         _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _I64P, _I64P,
         C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
@@ -401,6 +402,10 @@ class Context:
     check(self.lib.wb2_regrid_conservative(
         self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
         int(dst_stride), C.byref(a), C.byref(b)))
+
+  # -- derived variables -------------------------------------------------------
+  def wind_speed(self, u: int, v: int, out: int, n: int):
+    check(self.lib.wb2_wind_speed(self.handle, _P(u), _P(v), _P(out), int(n)))
 
   # -- K10 --------------------------------------------------------------------
   def rank_histogram(self, x: int, t: int, nmember: int, member_stride: int,

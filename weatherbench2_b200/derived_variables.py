@@ -151,3 +151,7 @@ class ZonalEnergySpectrum(DerivedVariable):
     if not is_torch:
       result = result.transpose(*ref_dims)
     return xl.to_xarray(result) if native else result
+
+
+# Wind variables live in _derived_wind.py (they need DerivedVariable).
+from weatherbench2_b200._derived_wind import WindSpeed  # noqa: E402  pylint: disable=wrong-import-position
