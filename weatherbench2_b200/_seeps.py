@@ -12,7 +12,6 @@ import typing as t
 import numpy as np
 import pandas as pd
 
-from weatherbench2_b200 import _lib
 from weatherbench2_b200 import _spatial as sp
 from weatherbench2_b200 import metrics as m
 from weatherbench2_b200 import xarray_lite as xl
