@@ -24,17 +24,17 @@ def nearest_neighbor_indices(source_grid: 'rg.Grid', target_grid: 'rg.Grid'
   """Haversine nearest-neighbour indices from source to target, the same
   BallTree query as regridding.py:212-228 (indices into the raveled
   (lon, lat) source slab)."""
-  from sklearn import neighbors  # pylint: disable=import-outside-toplevel
-  source_lat_rad = np.deg2rad(source_grid.latitudes)
-  source_lon_rad = np.deg2rad(source_grid.longitudes)
-  target_lat_rad = np.deg2rad(target_grid.latitudes)
-  target_lon_rad = np.deg2rad(target_grid.longitudes)
-  source_mesh = np.meshgrid(source_lat_rad, source_lon_rad)
-  target_mesh = np.meshgrid(target_lat_rad, target_lon_rad)
-  index_coords = np.stack([x.ravel() for x in source_mesh], axis=-1)
-  query_coords = np.stack([x.ravel() for x in target_mesh], axis=-1)
-  tree = neighbors.BallTree(index_coords, metric='haversine')
-  return tree.query(query_coords, return_distance=False).squeeze(axis=-1)
+  from sklearn.neighbors import BallTree  # pylint: disable=import-outside-toplevel
+
+  def points(grid):
+    # (lat, lon) in radians of every cell of the raveled (lon, lat) slab:
+    # index = i_lon * nlat + i_lat, like the reference's meshgrid + ravel
+    lat = np.deg2rad(np.asarray(grid.latitudes, dtype=np.float64))
+    lon = np.deg2rad(np.asarray(grid.longitudes, dtype=np.float64))
+    return np.column_stack([np.tile(lat, lon.size), np.repeat(lon, lat.size)])
+
+  tree = BallTree(points(source_grid), metric='haversine')
+  return tree.query(points(target_grid), k=1, return_distance=False)[:, 0]
 
 
 def interp_taps(x, xp, clamp: bool, period: Optional[float] = None):
