@@ -1,0 +1,105 @@
+"""More host-side logic that needs no GPU: the per-context call lock, threshold
+spec validation, SEEPS climatology handling, rank-histogram binning."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import test_threshold_metrics_gpu as thr_helpers
+import wb2_testdata as td
+
+
+def test_locked_lib_serialises_calls():
+  from weatherbench2_b200 import _lib
+
+  class FakeLib:
+    def __init__(self):
+      self.inside = 0
+      self.max_inside = 0
+
+    def wb2_work(self, x):
+      self.inside += 1
+      self.max_inside = max(self.max_inside, self.inside)
+      time.sleep(0.002)
+      self.inside -= 1
+      return x + 1
+
+  fake = FakeLib()
+  locked = _lib._LockedLib(fake, threading.RLock())  # pylint: disable=protected-access
+  out = []
+  threads = [threading.Thread(target=lambda i=i: out.append(locked.wb2_work(i)))
+             for i in range(16)]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  assert sorted(out) == list(range(1, 17))
+  assert fake.max_inside == 1
+  with pytest.raises(AttributeError):
+    locked.wb2_missing  # pylint: disable=pointless-statement
+
+
+def test_threshold_spec_validation():
+  from weatherbench2_b200 import _spatial as sp, _thresholded, thresholds
+  truth, _, clim, *_ = thr_helpers._random_case(None, False)  # pylint: disable=protected-access
+  tds = thr_helpers._ds(**truth)  # pylint: disable=protected-access
+  t_da = tds['geopotential']
+  layout = sp.prepare_operand(t_da, None, np.float32).layout
+  g1 = thresholds.GaussianQuantileThreshold(clim, 0.2)
+  g2 = thresholds.GaussianQuantileThreshold(clim, 0.8)
+  kind, m_op, s_op, z = _thresholded._threshold_spec(  # pylint: disable=protected-access
+      [g1, g2], tds, 'geopotential', t_da, layout)
+  assert kind == 'gaussian' and len(z) == 2 and z[0] < 0 < z[1]
+  assert m_op.nrow == s_op.nrow
+  with pytest.raises(ValueError, match='at least one'):
+    _thresholded._threshold_spec([], tds, 'geopotential', t_da, layout)  # pylint: disable=protected-access
+  other = thr_helpers._ds(  # pylint: disable=protected-access
+      {k: (clim[k].dims, np.asarray(clim[k].values)) for k in clim.keys()},
+      {k: np.asarray(c.values) for k, c in clim.coords.items()})
+  g3 = thresholds.GaussianQuantileThreshold(other, 0.5)
+  with pytest.raises(ValueError, match='share'):
+    _thresholded._threshold_spec([g1, g3], tds, 'geopotential', t_da, layout)  # pylint: disable=protected-access
+  # the metric classes keep the reference's positional signature
+  from weatherbench2_b200 import metrics
+  m = metrics.EnsembleBrierScore([g1, g2])
+  assert m.thresholds == [g1, g2] and m.ensemble_dim == 'realization'
+  assert metrics.GaussianRPS([g1]).thresholds == [g1]
+  assert metrics.EnsembleBrierScore([g1], 'number').ensemble_dim == 'number'
+
+
+def test_seeps_climatology_handling():
+  import test_seeps_gpu as seeps_helpers
+  from weatherbench2_b200 import _seeps, evaluation, metrics
+  fds, tds, _, truth = seeps_helpers._pair(nday=4)  # pylint: disable=protected-access
+  rs = np.random.RandomState(0)
+  clim, frac, _ = seeps_helpers._climatology(truth, 0, 0, rs)  # pylint: disable=protected-access
+  s = metrics.SpatialSEEPS(climatology=clim)
+  np.testing.assert_allclose(np.asarray(s.p1.values), frac.mean(axis=(0, 1)),
+                             rtol=1e-6)
+  assert set(s.p1.dims) == {'latitude', 'longitude'}
+  tsel = evaluation.select_truth_at_valid_time(tds, fds)
+  wet = clim[seeps_helpers.NAME + '_seeps_threshold']
+  maps = _seeps._threshold_maps(wet, fds[seeps_helpers.NAME])  # pylint: disable=protected-access
+  assert set(maps) == {'dayofyear', 'hour'}
+  dims, pos = maps['dayofyear']
+  assert dims == ('init_time', 'lead_time')
+  np.testing.assert_array_equal(pos[:, 0], np.arange(4))  # 1..4 January
+  np.testing.assert_array_equal(maps['hour'][1], 0)
+  tmaps = _seeps._threshold_maps(wet, tsel[seeps_helpers.NAME])  # pylint: disable=protected-access
+  np.testing.assert_array_equal(tmaps['dayofyear'][1], pos)
+  with pytest.raises(KeyError):
+    _seeps._threshold_maps(wet.isel(hour=0), fds[seeps_helpers.NAME])  # pylint: disable=protected-access
+
+
+def test_rank_histogram_binning_rules():
+  from weatherbench2_b200 import metrics
+  assert metrics.RankHistogram()._num_bins_actual(9) == 10  # pylint: disable=protected-access
+  assert metrics.RankHistogram(num_bins=5)._num_bins_actual(9) == 5  # pylint: disable=protected-access
+  with pytest.raises(ValueError, match='Cannot bin'):
+    metrics.RankHistogram(num_bins=4)._num_bins_actual(9)  # pylint: disable=protected-access
+  rh = metrics.RankHistogram(ensemble_dim='number', seed=3)
+  assert rh.ensemble_dim == 'number' and rh._seed == 3  # pylint: disable=protected-access
+  truth, forecast = td.get_random_truth_and_forecast(ensemble_size=None)
+  with pytest.raises(ValueError):  # no ensemble dimension (metrics.py:574-577)
+    rh.compute_chunk(thr_helpers._ds(**forecast), thr_helpers._ds(**truth))  # pylint: disable=protected-access
