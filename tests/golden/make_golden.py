@@ -60,6 +60,95 @@ GOLDEN = {
         'cases': [[1, 0, 1], [-1, 0, -1], [5, 0, 5], [6, 0, -4], [1, 9, 11],
                   [5, 9, 5]],
     },
+    # --- probabilistic / threshold / categorical metrics ----------------------
+    # mock data are constant fields, so the point-wise score IS the average
+    'gaussian_crps': {
+        'source': 'weatherbench2/metrics_test.py:286-304',
+        'forecast_mean': 1.0, 'forecast_std': 1.0, 'truth': 1.02,
+        'expected': 0.23385455,
+    },
+    'gaussian_brier': {
+        'source': 'weatherbench2/metrics_test.py:370-431',
+        'truth': 1.0, 'clim_mean': 1.0, 'clim_std': 1.0, 'quantile': 0.8,
+        # forecast mean = forecast std = 1 + error
+        'cases': [{'error': 0.02, 'gaussian_quantile': 0.04421,
+                   'quantile': 0.257883},
+                  {'error': 1e6, 'gaussian_quantile': 0.70786,
+                   'quantile': 0.707861}],
+        'rtol': 1e-4,
+    },
+    'gaussian_ignorance': {
+        'source': 'weatherbench2/metrics_test.py:436-475',
+        'truth': 1.0, 'clim_mean': 1.0, 'clim_std': 1.0, 'quantile': 0.8,
+        'cases': [{'error': 0.02, 'expected': 0.236055},
+                  {'error': 1e6, 'expected': 1.841019}],
+        'rtol': 1e-4,
+    },
+    'gaussian_rps': {
+        'source': 'weatherbench2/metrics_test.py:480-534',
+        'truth': 1.0, 'thresholds': [0.0, 1.0, 2.0],
+        'cases': [{'error': 0.02, 'expected': 0.295746},
+                  {'error': 1e6, 'expected': 0.758203}],
+        'rtol': 1e-4,
+    },
+    'ensemble_brier': {
+        'source': 'weatherbench2/metrics_test.py:989-1029',
+        'truth': 1.0, 'clim_mean': 1.0, 'clim_std': 1.0, 'quantile': 0.2,
+        'member_offsets': [-2, -1, 0, 1],
+        # members = 1 + error + ens_delta * member_offsets
+        'cases': [{'error': 0.0, 'ens_delta': 0.1, 'expected': 0.0},
+                  {'error': 0.0, 'ens_delta': 1.0, 'expected': 0.25},
+                  {'error': -10.0, 'ens_delta': 0.1, 'expected': 1.0}],
+    },
+    'ensemble_ignorance': {
+        'source': 'weatherbench2/metrics_test.py:1294-1329',
+        'truth': 1.0, 'clim_mean': 1.0, 'clim_std': 1.0, 'quantile': 0.2,
+        'nmember': 4,
+        'cases': [{'error': 0.0, 'expected': 0.0},
+                  {'error': -10.0, 'expected': 'inf'}],
+    },
+    'ensemble_rps': {
+        'source': 'weatherbench2/metrics_test.py:1334-1390',
+        'truth': 1.5, 'thresholds': [0.0, 1.0, 2.0], 'nmember': 4,
+        'cases': [{'error': 0.02, 'expected': 0.0},
+                  {'error': -2.0, 'expected': 2.0}],
+    },
+    'seeps': {
+        'source': 'weatherbench2/metrics_test.py:1392-1440',
+        'dry_fraction': 0.4, 'wet_threshold': 1.0, 'truth': 0.0,
+        'cases': [{'forecast': 0.0, 'expected': 0.0},
+                  {'forecast': 0.5, 'expected': 1.25}],
+        'atol': 1e-4,
+    },
+    # --- nearest / bilinear regridders ------------------------------------------
+    'bilinear_longitude_periodicity': {
+        'source': 'weatherbench2/regridding_test.py:495-525',
+        'source_lon': [0.0, 90.0, 180.0, 270.0],
+        'target_lon': [45.0, 135.0, 225.0, 315.0],
+        'field': [[0.0], [1.0], [2.0], [3.0]],
+        'periodic': [[0.5], [1.5], [2.5], [1.5]],
+        'not_periodic': [[0.5], [1.5], [2.5], [None]],
+    },
+    'bilinear_latitude_poles': {
+        'source': 'weatherbench2/regridding_test.py:527-572',
+        'cases': [
+            {'poles': True, 'source_lat': [-90.0, -30.0, 30.0, 90.0],
+             'target_lat': [-60.0, 0.0, 60.0], 'field': [0.0, 1.0, 2.0, 3.0],
+             'expected': [[0.5, 1.5, 2.5]]},
+            {'poles': True, 'source_lat': [-60.0, 0.0, 60.0],
+             'target_lat': [-90.0, -30.0, 30.0, 90.0],
+             'field': [0.0, 1.0, 2.0], 'expected': [[0.0, 0.5, 1.5, 2.0]]},
+            {'poles': False, 'source_lat': [-60.0, -20.0, 20.0, 60.0],
+             'target_lat': [-70.0, 0.0, 70.0], 'field': [0.0, 1.0, 2.0, 3.0],
+             'expected': [[None, 1.5, None]]}],
+    },
+    'nearest_exact': {
+        'source': 'weatherbench2/regridding_test.py:574-591',
+        'source_lon': [0, 90, 180, 270], 'source_lat': [-30, 0, 30],
+        'target_lon': [0, 180], 'target_lat': [-30, 0, 30],
+        'field': [[0, 1, 2], [4, 5, 6], [7, 8, 9], [10, 11, 12]],
+        'expected': [[0, 1, 2], [7, 8, 9]],
+    },
 }
 
 if __name__ == '__main__':
