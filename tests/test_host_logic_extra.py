@@ -103,3 +103,31 @@ def test_rank_histogram_binning_rules():
   truth, forecast = td.get_random_truth_and_forecast(ensemble_size=None)
   with pytest.raises(ValueError):  # no ensemble dimension (metrics.py:574-577)
     rh.compute_chunk(thr_helpers._ds(**forecast), thr_helpers._ds(**truth))  # pylint: disable=protected-access
+
+
+def test_time_mean_accumulator_with_map_and_quantile_outputs():
+  """Chunked time means of map-output / threshold results (extra `quantile`,
+  `bins`, latitude / longitude dims) equal the unchunked mean, NaN-aware."""
+  from weatherbench2_b200 import distributed, xarray_lite as xl
+  rs = np.random.RandomState(0)
+  dims = ('quantile', 'init_time', 'lead_time', 'latitude', 'longitude')
+  full = rs.normal(size=(3, 6, 2, 5, 8))
+  full[rs.uniform(size=full.shape) < 0.1] = np.nan
+  full[:, :, 0, 0, 0] = np.nan  # a cell that is NaN in every chunk
+  coords = {'quantile': np.array([0.1, 0.5, 0.9]), 'init_time': np.arange(6),
+            'lead_time': np.arange(2), 'latitude': np.linspace(-60, 60, 5),
+            'longitude': np.arange(8) * 45.0}
+  for skipna in (False, True):
+    acc = distributed.TimeMeanAccumulator('init_time', skipna)
+    for i0 in range(0, 6, 2):
+      chunk = {k: (v[i0:i0 + 2] if k == 'init_time' else v)
+               for k, v in coords.items()}
+      acc.add(xl.Dataset({'z': (dims, full[:, i0:i0 + 2])}, chunk))
+    got = acc.finish()['z']
+    assert got.dims == ('quantile', 'lead_time', 'latitude', 'longitude')
+    import warnings
+    with warnings.catch_warnings():
+      warnings.simplefilter('ignore', RuntimeWarning)
+      want = np.nanmean(full, axis=1) if skipna else full.mean(axis=1)
+    np.testing.assert_allclose(got.values, want, rtol=1e-12, equal_nan=True)
+    assert np.isnan(got.values[:, 0, 0, 0]).all()
