@@ -208,6 +208,12 @@ def bench_spectrum(args):
   ms = timeit(fn, args.steps)
   report('zonal_spectrum time-summed output', ms, cells * 4, cells,
          'grid_cells')
+  red = torch.zeros((13, nk), device='cuda', dtype=torch.float32)
+  fn = lambda: ctx.zonal_spectrum_latsum(x.data_ptr(), nfield, NLAT, NLON,
+                                         scale, red.data_ptr(), 13)
+  ms = timeit(fn, args.steps)
+  report('zonal_spectrum + latitude-weighted reduction (latsum)', ms,
+         cells * 4, cells, 'grid_cells')
 
 
 def bench_maps(args):

@@ -382,6 +382,23 @@ int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield,
                        int32_t nrow, int32_t ncol, const double* scale,
                        float* out, int32_t accumulate, int64_t nfield_out);
 
+/* K4 with the weighted meridional reduction fused in (BASELINE north star: "a
+ * shared-memory rFFT along longitude followed by a weighted meridional
+ * reduction").  The reference keeps `latitude` (derived_variables.py:592-626);
+ * its callers average the per-latitude spectra over latitude bands afterwards,
+ * so the reduction is defined on the reference's own output:
+ *     out[slot][k] = sum_{fields i of the slot} sum_row scale[row] * S_ref[i][row][k]
+ * where S_ref is the spectrum WITHOUT the circumference factor, i.e. the caller
+ * passes scale[row] = circumference(row) * w(row) with w the (normalised)
+ * latitude weight of weatherbench2/metrics.py:40-60 (or a latitude-band mask
+ * times it).  Fields are slot-minor like wb2_zonal_spectrum's accumulate mode
+ * (field i belongs to slot i % nfield_out), so a time mean is the same call.
+ *   out    device [nfield_out][ncol/2+1] float32, overwritten
+ * The per-latitude spectrum is never written: 4 B read per cell, ~0 written. */
+int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
+                              int32_t nrow, int32_t ncol, const double* scale,
+                              float* out, int64_t nfield_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,9 @@ PROTOTYPES = {
     'wb2_zonal_spectrum': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32,
                                      C.POINTER(C.c_double), _P, C.c_int32,
                                      C.c_int64]),
+    'wb2_zonal_spectrum_latsum': (C.c_int, [_P, _P, C.c_int64, C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_double),
+                                            _P, C.c_int64]),
 }
 
 
@@ -472,6 +475,16 @@ class Context:
         self.handle, _P(x), int(nfield), int(nrow), int(ncol),
         _as_ptr(scale, C.c_double), _P(out), int(bool(accumulate)),
         int(nfield_out)))
+
+
+  def zonal_spectrum_latsum(self, x: int, nfield: int, nrow: int, ncol: int,
+                            scale: np.ndarray, out: int, nfield_out: int):
+    """out[slot][k] = sum over the slot's fields and over rows of
+    scale[row] * spectrum (scale = circumference * latitude weight)."""
+    scale = np.ascontiguousarray(scale, dtype=np.float64)
+    check(self.lib.wb2_zonal_spectrum_latsum(
+        self.handle, _P(x), int(nfield), int(nrow), int(ncol),
+        _as_ptr(scale, C.c_double), _P(out), int(nfield_out)))
 
 
 class WeightSpec:

@@ -474,9 +474,63 @@ static bool factorize(int n2, int* radix, int* nstage) {
   return true;
 }
 
+// spectrum_pfa.cu: prime-factor / packed-f32x2 / TMA kernel for 1440, 720 and 240
+// longitudes (1 = handled, 0 = not eligible, < 0 = error)
+int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow, int32_t ncol,
+                     const double* scale, float* out, int mode, int64_t nslot);
+
+// out[slot][k] = sum_row spec[slot][row][k]   (rows already carry their weights)
+__global__ void latsum_rows_kernel(const float* __restrict__ spec, float* __restrict__ out,
+                                   int64_t nslot, int nrow, int nk) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= nslot * nk) return;
+  const int64_t slot = i / nk;
+  const int k = static_cast<int>(i - slot * nk);
+  float s = 0.f;
+  for (int r = 0; r < nrow; ++r) s += spec[(slot * nrow + r) * int64_t(nk) + k];
+  out[i] = s;
+}
+
 }  // namespace wb2
 
 using namespace wb2;
+
+extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
+                                         int32_t nrow, int32_t ncol, const double* scale,
+                                         float* out, int64_t nfield_out) {
+  WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
+  WB2_REQUIRE(nrow > 0 && ncol > 1, "bad grid %d x %d", nrow, ncol);
+  WB2_REQUIRE(nfield >= 0, "nfield < 0");
+  if (nfield == 0) return WB2_OK;
+  WB2_REQUIRE(x && out && scale, "NULL argument");
+  WB2_REQUIRE(nfield_out > 0 && nfield % nfield_out == 0,
+              "nfield (%lld) must be a multiple of nfield_out (%lld)",
+              static_cast<long long>(nfield), static_cast<long long>(nfield_out));
+  DeviceGuard guard(ctx->device);
+  const int prc = spectrum_pfa_try(ctx, x, nfield, nrow, ncol, scale, out, 2, nfield_out);
+  if (prc != 0) return prc < 0 ? prc : WB2_OK;
+  // other row lengths / unaligned data: per-row spectra (time-summed) into
+  // scratch, then the row sum
+  const int nk = ncol / 2 + 1;
+  const size_t need = size_t(nfield_out) * nrow * nk * sizeof(float);
+  if (need > ctx->scratch_cap) {
+    WB2_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) WB2_CUDA_TRY(cudaFree(ctx->scratch));
+    ctx->scratch = nullptr;
+    ctx->scratch_cap = 0;
+    WB2_CUDA_TRY(cudaMalloc(&ctx->scratch, need));
+    ctx->scratch_cap = need;
+  }
+  float* spec = static_cast<float*>(ctx->scratch);
+  WB2_CUDA_TRY(cudaMemsetAsync(spec, 0, need, ctx->stream));
+  WB2_TRY(wb2_zonal_spectrum(ctx, x, nfield, nrow, ncol, scale, spec, 1, nfield_out));
+  const int64_t n = nfield_out * nk;
+  latsum_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+      spec, out, nfield_out, nrow, nk);
+  WB2_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 1;
+  return WB2_OK;
+}
 
 extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
                                   int32_t ncol, const double* scale, float* out,
@@ -504,6 +558,17 @@ extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, 
     return WB2_EUNSUPPORTED;
   }
   DeviceGuard guard(ctx->device);
+  {
+    const int prc = spectrum_pfa_try(ctx, x, nfield, nrow, ncol, scale, out,
+                                     accumulate ? 1 : 0, nfield_out);
+    if (prc != 0) return prc < 0 ? prc : WB2_OK;
+    const char* force = getenv("WB2_SPECTRUM_PATH");
+    if (force && strcmp(force, "pfa") == 0) {  // tests: fail instead of falling back
+      set_error("wb2_zonal_spectrum: WB2_SPECTRUM_PATH=pfa but %d longitudes / this "
+                "alignment are not eligible for the prime-factor kernel", ncol);
+      return WB2_EUNSUPPORTED;
+    }
+  }
 
   // host tables in double precision, rounded once to float32
   std::vector<float2> tw2(p.n2), twn(p.n2 + 1);
