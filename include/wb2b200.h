@@ -108,6 +108,18 @@ int wb2_destroy(wb2_ctx* ctx);
 int wb2_set_stream(wb2_ctx* ctx, void* cuda_stream);
 void* wb2_get_stream(wb2_ctx* ctx);
 int wb2_synchronize(wb2_ctx* ctx);
+/* Ordering with a caller-owned stream WITHOUT blocking the host (the context's
+ * own stream is cudaStreamNonBlocking, so nothing orders it implicitly against
+ * e.g. torch's current stream):
+ *   wb2_wait_stream : work enqueued on the context AFTER this call waits for
+ *                     everything already enqueued on `cuda_stream` (inputs
+ *                     still being produced there);
+ *   wb2_stream_wait : work enqueued on `cuda_stream` AFTER this call waits for
+ *                     everything already enqueued on the context (results).
+ * No-ops when `cuda_stream` is the context's stream (wb2_set_stream).  NULL is
+ * the legacy default stream.                                                  */
+int wb2_wait_stream(wb2_ctx* ctx, void* cuda_stream);
+int wb2_stream_wait(wb2_ctx* ctx, void* cuda_stream);
 
 int wb2_malloc(wb2_ctx* ctx, size_t bytes, void** dev_ptr);
 int wb2_free(wb2_ctx* ctx, void* dev_ptr);

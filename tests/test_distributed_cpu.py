@@ -107,3 +107,44 @@ def test_single_process_without_process_group():
   np.testing.assert_allclose(res['z'].values, full.values.mean(axis=0),
                              rtol=1e-12)
   assert res['z'].dims == ('lead_time',)
+
+
+def test_by_valid_chunks_align_truth_by_label_not_position():
+  """chunk_dim='time': the truth record is longer than the forecast's and
+  starts earlier; chunks must pick the truth of the SAME time labels
+  (the reference aligns by label; ADVICE r1: positional slicing paired
+  forecast chunks with the wrong truth)."""
+  rs = np.random.RandomState(3)
+  nlat, nlon = 5, 8
+  lat = np.linspace(-90, 90, nlat)
+  lon = np.linspace(0, 360, nlon, endpoint=False)
+  ttimes = (np.datetime64('2020-01-01', 'ns') +
+            np.arange(12) * np.timedelta64(1, 'D'))
+  ftimes = ttimes[4:9]  # starts 4 days into the truth record
+  f = rs.normal(size=(5, nlat, nlon)).astype(np.float32)
+  t = rs.normal(size=(12, nlat, nlon)).astype(np.float32)
+  dims = ('time', 'latitude', 'longitude')
+  forecast = xl.Dataset({'z': (dims, f)}, {'time': ftimes, 'latitude': lat,
+                                           'longitude': lon})
+  truth = xl.Dataset({'z': (dims, t)}, {'time': ttimes, 'latitude': lat,
+                                        'longitude': lon})
+
+  def loop(fc, tr, eval_config, skipna, compute_chunk=True):
+    from oracle import wb2_oracle as orc
+    del eval_config, compute_chunk
+    np.testing.assert_array_equal(fc['time'].values, tr['time'].values)
+    r, d = orc.mse(fc['z'].values, fc['z'].dims, tr['z'].values, tr['z'].dims,
+                   lat, lon, skipna=skipna)
+    return xl.Dataset({'z': (d, r)}, {'time': fc['time'].values})
+
+  res = wd.evaluate_sharded(forecast, truth, None, chunk_dim='time',
+                            chunk_size=2, loop_fn=loop)
+  from oracle import wb2_oracle as orc
+  want, _ = orc.mse(f, dims, t[4:9], dims, lat, lon)
+  np.testing.assert_allclose(res['z'].values, want.mean(), rtol=1e-12)
+  # a forecast time the truth does not have is an error, not a silent drop
+  bad = xl.Dataset({'z': (dims, f)},
+                   {'time': ftimes + np.timedelta64(100, 'D'),
+                    'latitude': lat, 'longitude': lon})
+  with pytest.raises(KeyError):
+    wd.evaluate_sharded(bad, truth, None, chunk_dim='time', loop_fn=loop)

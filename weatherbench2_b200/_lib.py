@@ -75,6 +75,8 @@ PROTOTYPES = {
     'wb2_set_stream': (C.c_int, [_P, _P]),
     'wb2_get_stream': (_P, [_P]),
     'wb2_synchronize': (C.c_int, [_P]),
+    'wb2_wait_stream': (C.c_int, [_P, _P]),
+    'wb2_stream_wait': (C.c_int, [_P, _P]),
     'wb2_malloc': (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     'wb2_free': (C.c_int, [_P, _P]),
     'wb2_host_alloc': (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
@@ -176,25 +178,71 @@ def _as_ptr(a: Optional[np.ndarray], ctype):
   return a.ctypes.data_as(C.POINTER(ctype))
 
 
+# entry points that enqueue kernels (or staged copies) on the context's stream
+_COMPUTE = frozenset(n for n in PROTOTYPES if n not in (
+    'wb2_version', 'wb2_last_error', 'wb2_has_cuda', 'wb2_launch_count',
+    'wb2_create', 'wb2_destroy', 'wb2_set_stream', 'wb2_get_stream',
+    'wb2_synchronize', 'wb2_wait_stream', 'wb2_stream_wait', 'wb2_malloc',
+    'wb2_free', 'wb2_host_alloc', 'wb2_host_free'))
+
+
+def _torch_current_stream(device: int):
+  """cudaStream_t of torch's current stream on `device`, or None when torch
+  has not been imported / has no CUDA context (nothing to order against)."""
+  import sys  # pylint: disable=import-outside-toplevel
+  torch = sys.modules.get('torch')
+  if torch is None:
+    return None
+  try:
+    if not (torch.cuda.is_available() and torch.cuda.is_initialized()):
+      return None
+    return int(torch.cuda.current_stream(device).cuda_stream)
+  except Exception:  # pylint: disable=broad-except
+    return None
+
+
 class _LockedLib:
   """The library with every call into it serialised by the context's lock.  A
   wb2_ctx (stream, descriptor slots, scratch) is not re-entrant, ctypes drops
   the GIL during a call, and the reference's callers may evaluate chunks from
   several threads (Beam DirectRunner, weatherbench2/evaluation.py:697, 733)
   against the process-wide default context.  Error strings are thread-local
-  on the C side, so `check()` may read them after the lock is released."""
+  on the C side, so `check()` may read them after the lock is released.
 
-  def __init__(self, lib, lock):
+  Stream ordering: the context's stream is non-blocking, so nothing orders it
+  implicitly against torch's streams.  Every compute entry point is therefore
+  bracketed by wb2_wait_stream / wb2_stream_wait on torch's CURRENT stream
+  (device-side event waits, no host blocking): kernels see inputs that torch
+  is still producing, and torch consumers / `.cpu()` see finished outputs.
+  Both are no-ops when the context shares torch's stream (bench.py)."""
+
+  def __init__(self, lib, lock, owner=None):
     self._lib = lib
     self._lock = lock
+    self._owner = owner
 
   def __getattr__(self, name):
     fn = getattr(self._lib, name)
     lock = self._lock
+    if name in _COMPUTE and self._owner is not None:
+      owner, raw = self._owner, self._lib
 
-    def call(*args):
-      with lock:
-        return fn(*args)
+      def call(*args):
+        with lock:
+          s = _torch_current_stream(owner.device)
+          if s is None:
+            return fn(*args)
+          rc = raw.wb2_wait_stream(owner.handle, _P(s))
+          if rc != 0:
+            return rc
+          rc = fn(*args)
+          rc2 = raw.wb2_stream_wait(owner.handle, _P(s))
+          return rc if rc != 0 else rc2
+    else:
+
+      def call(*args):
+        with lock:
+          return fn(*args)
 
     call.__name__ = name
     setattr(self, name, call)  # cache: __getattr__ only runs on a miss
@@ -207,11 +255,11 @@ class Context:
 
   def __init__(self, device: int = 0):
     self._lock = threading.RLock()
-    self.lib = _LockedLib(load_library(), self._lock)
+    self.device = int(device)
+    self.lib = _LockedLib(load_library(), self._lock, self)
     h = _P()
     check(self.lib.wb2_create(int(device), C.byref(h)))
     self.handle = h
-    self.device = int(device)
     self._closed = False
 
   def close(self):

@@ -135,6 +135,8 @@ int wb2_destroy(wb2_ctx* c) {
     if (c->stage_copied[i]) cudaEventDestroy(c->stage_copied[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
   }
+  if (c->order_in) cudaEventDestroy(c->order_in);
+  if (c->order_out) cudaEventDestroy(c->order_out);
   if (c->d_out_tmp) cudaFree(c->d_out_tmp);
   if (c->tma_partial) cudaFree(c->tma_partial);
   if (c->scratch) cudaFree(c->scratch);
@@ -165,6 +167,31 @@ int wb2_synchronize(wb2_ctx* c) {
   WB2_REQUIRE(c != nullptr, "ctx is NULL");
   DeviceGuard g(c->device);
   WB2_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return WB2_OK;
+}
+
+int wb2_wait_stream(wb2_ctx* c, void* cuda_stream) {
+  WB2_REQUIRE(c != nullptr, "ctx is NULL");
+  cudaStream_t other = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (other == c->stream) return WB2_OK;  // same stream: already ordered
+  DeviceGuard g(c->device);
+  if (!c->order_in)
+    WB2_CUDA_TRY(cudaEventCreateWithFlags(&c->order_in, cudaEventDisableTiming));
+  WB2_CUDA_TRY(cudaEventRecord(c->order_in, other));
+  WB2_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->order_in, 0));
+  WB2_CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->order_in, 0));
+  return WB2_OK;
+}
+
+int wb2_stream_wait(wb2_ctx* c, void* cuda_stream) {
+  WB2_REQUIRE(c != nullptr, "ctx is NULL");
+  cudaStream_t other = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (other == c->stream) return WB2_OK;
+  DeviceGuard g(c->device);
+  if (!c->order_out)
+    WB2_CUDA_TRY(cudaEventCreateWithFlags(&c->order_out, cudaEventDisableTiming));
+  WB2_CUDA_TRY(cudaEventRecord(c->order_out, c->stream));
+  WB2_CUDA_TRY(cudaStreamWaitEvent(other, c->order_out, 0));
   return WB2_OK;
 }
 

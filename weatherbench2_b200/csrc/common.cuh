@@ -78,6 +78,9 @@ struct wb2_ctx {
   // generic scratch of the other kernels (grown on demand)
   void* scratch = nullptr;
   size_t scratch_cap = 0;
+  // cross-stream ordering with a caller's stream (wb2_wait_stream / wb2_stream_wait)
+  cudaEvent_t order_in = nullptr;
+  cudaEvent_t order_out = nullptr;
 };
 
 namespace wb2 {

@@ -269,9 +269,9 @@ constexpr int idem(int n2, int r) {  // CRT idempotent: 1 mod r, 0 mod n2 / r
   return x % n2;
 }
 
-template <int RA_, int RB_, int RC_, int G_, int NT_>
+template <int RA_, int RB_, int RC_, int G_, int NT_, int MINB_ = 2>
 struct Plan {
-  static constexpr int RA = RA_, RB = RB_, RC = RC_, G = G_, NT = NT_;
+  static constexpr int RA = RA_, RB = RB_, RC = RC_, G = G_, NT = NT_, MINB = MINB_;
   static constexpr int N2 = RA * RB * RC, NK = N2 + 1, N = 2 * N2;
   static constexpr int SA = N2 / RA, SB = N2 / RB, SC = N2 / RC;  // Good's input map
   static constexpr int EA = idem(N2, RA), EB = idem(N2, RB), EC = idem(N2, RC);
@@ -287,8 +287,11 @@ struct Plan {
   static constexpr int kTwnBytes = N2 * 16;
   static constexpr int kTaskBytes = ((NTC * 16 + 127) / 128) * 128;
   static constexpr int kSmem = kStageBytes + kWorkBytes + kTwnBytes + kTaskBytes + 64;
-  static_assert(G * NTC <= NT, "stage C keeps one task per thread (register accumulators)");
-  static_assert(G * NTA <= NT && G * NTB <= NT, "one task per thread in every stage");
+  // thread slots per row pair, padded to half-warps so that the 64-bit shared
+  // accesses of a half-warp stay inside one row pair (conflict-free strides)
+  static constexpr int PTB = (NTB + 15) / 16 * 16, PTC = (NTC + 15) / 16 * 16;
+  static_assert(G * PTC <= NT, "stage C keeps one task per thread (register accumulators)");
+  static_assert(G * NTA <= NT && G * PTB <= NT, "one task per thread in every stage");
   static_assert(2 * G * NK * 4 <= kWorkBytes, "flush tile must fit the work buffer");
   static_assert(N2 % 2 == 0, "rows must be multiples of 16 bytes for TMA");
 };
@@ -353,7 +356,7 @@ __device__ __forceinline__ void issue_item(const Params& p, const Cursor& c, flo
 }
 
 template <class P, int MODE>
-__global__ void __launch_bounds__(P::NT, 2) spectrum_pfa_kernel(const Params p) {
+__global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Params p) {
   constexpr int RA = P::RA, RB = P::RB, RC = P::RC, G = P::G, NT = P::NT;
   constexpr int N2 = P::N2, NK = P::NK;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -401,18 +404,18 @@ __global__ void __launch_bounds__(P::NT, 2) spectrum_pfa_kernel(const Params p) 
     a_dst = g * N2 + nB * P::LB + nC;
   }
   // stage B (radix RB, in place): consecutive threads, consecutive elements
-  const bool b_on = tid < G * P::NTB;
+  bool b_on;
   int b_off = 0;
   {
-    const int g = tid / P::NTB, r = tid - g * P::NTB;
+    const int g = tid / P::PTB, r = tid - g * P::PTB;
+    b_on = g < G && r < P::NTB;
     b_off = g * N2 + r;
   }
   // stage C (radix RC on a butterfly and its mirror, then the real-input split)
-  const bool c_on = tid < G * P::NTC;
-  int c_g = 0, c_off1 = 0, c_off2 = 0, c_k0 = 0, c_self = 0;
+  int c_g = tid / P::PTC, c_off1 = 0, c_off2 = 0, c_k0 = 0, c_self = 0;
+  const bool c_on = c_g < G && tid - c_g * P::PTC < P::NTC;
   if (c_on) {
-    c_g = tid / P::NTC;
-    const int4 t = ctask[tid - c_g * P::NTC];
+    const int4 t = ctask[tid - c_g * P::PTC];
     c_off1 = c_g * N2 + t.x;
     c_off2 = c_g * N2 + t.y;
     c_k0 = t.z;
@@ -580,8 +583,11 @@ static void build_tables(std::vector<float4>* twn, std::vector<int4>* ctask) {
   }
   ctask->clear();
   std::vector<char> seen(P::RA * P::RB, 0);
-  for (int kA = 0; kA < P::RA; ++kA)
+  // kA = 1, 2, ... first: their kB runs are whole half-warps (16 consecutive kB
+  // hit 16 distinct bank pairs because LB is odd); the shorter kA = 0 run last
+  for (int ia = 1; ia <= P::RA; ++ia)
     for (int kB = 0; kB < P::RB; ++kB) {
+      const int kA = ia % P::RA;
       if (seen[kA * P::RB + kB]) continue;
       const int qA = (P::RA - kA) % P::RA, qB = (P::RB - kB) % P::RB;
       seen[kA * P::RB + kB] = 1;
@@ -614,7 +620,7 @@ static int launch(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
   p.ngroup = (npair + P::G - 1) / P::G;
   p.mode = mode;
   // latitude chunks of mode 2: enough jobs to fill the machine, few partials
-  const int64_t want_jobs = int64_t(ctx->num_sms) * 2 * 4;
+  const int64_t want_jobs = int64_t(ctx->num_sms) * P::MINB * 4;
   if (mode == 2) {
     int nchunk = static_cast<int>((want_jobs + nslot - 1) / nslot);
     if (nchunk < 1) nchunk = 1;
@@ -644,7 +650,7 @@ static int launch(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
   p.scale = pk.dev<float>(o3);
   p.out = mode == 2 ? pk.dev<float>(o4) : out;
 
-  const int64_t max_cta = int64_t(ctx->num_sms) * 2;
+  const int64_t max_cta = int64_t(ctx->num_sms) * P::MINB;
   const unsigned grid = static_cast<unsigned>(p.njob < max_cta ? p.njob : max_cta);
   auto kernel = mode == 0 ? spectrum_pfa_kernel<P, 0>
                           : (mode == 1 ? spectrum_pfa_kernel<P, 1> : spectrum_pfa_kernel<P, 2>);
@@ -679,8 +685,19 @@ int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
   if (nrow < 1 || nfield < 1 || nslot < 1 || nfield % nslot != 0) return 0;
   int rc;
   switch (ncol) {
-    case 1440: rc = pfa::launch<pfa::Plan<9, 16, 5, 3, 256>>(ctx, x, nfield, nrow, scale, out,
-                                                              mode, nslot); break;
+    case 1440: {
+      const char* plan = getenv("WB2_PFA_PLAN");  // experiments: CTA shape
+      if (plan && plan[0] == '0')
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 3, 256, 2>>(ctx, x, nfield, nrow, scale, out, mode,
+                                                         nslot);
+      else if (plan && plan[0] == '2')
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 1, 96, 5>>(ctx, x, nfield, nrow, scale, out, mode,
+                                                        nslot);
+      else  // default: 3 CTAs of 5 warps per SM (measured best)
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 3>>(ctx, x, nfield, nrow, scale, out, mode,
+                                                         nslot);
+      break;
+    }
     case 720: rc = pfa::launch<pfa::Plan<9, 8, 5, 5, 256>>(ctx, x, nfield, nrow, scale, out,
                                                             mode, nslot); break;
     case 240: rc = pfa::launch<pfa::Plan<3, 8, 5, 6, 256>>(ctx, x, nfield, nrow, scale, out,

@@ -107,6 +107,18 @@ class TimeMeanAccumulator:
     return out
 
 
+def _truth_for_chunk(truth, fc, chunk_dim, select_truth):
+  """Truth of one forecast chunk.  By-valid chunks (`chunk_dim == 'time'`) are
+  aligned BY LABEL like the reference's xarray arithmetic -- the truth record
+  may be longer than the forecast's or start elsewhere -- never by position;
+  forecast times without a truth label raise KeyError (an inner join would
+  silently shorten the time mean)."""
+  tr = select_truth(truth, fc)
+  if chunk_dim == 'time' and 'time' in truth.dims and 'time' in fc.coords:
+    tr = truth.sel(time=fc.coords['time'].values)
+  return tr
+
+
 def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
                      skipna: bool = False, chunk_dim: str = 'init_time',
                      chunk_size: int = 1, group=None, device=None,
@@ -139,17 +151,13 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   for ci in shard_indices(nchunks, rank, world):
     sl = slice(int(ci) * chunk_size, min(n, (int(ci) + 1) * chunk_size))
     fc = forecast.isel({chunk_dim: sl})
-    tr = select_truth(truth, fc)
-    if chunk_dim == 'time' and 'time' in truth.dims:
-      tr = truth.isel(time=sl)
+    tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
     acc.add(loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True))
   if not acc.sums:
     # a rank without chunks still has to take part in the collective with the
     # right payload shape: evaluate nothing, contribute zeros
     fc = forecast.isel({chunk_dim: slice(0, 1)})
-    tr = select_truth(truth, fc)
-    if chunk_dim == 'time' and 'time' in truth.dims:
-      tr = truth.isel(time=slice(0, 1))
+    tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
     probe = loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True)
     acc.add(probe)
     for k in acc.sums:
