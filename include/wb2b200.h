@@ -168,6 +168,32 @@ int wb2_det_metrics_host(wb2_ctx* ctx, const void* f, const void* t,
                          const int64_t* off_c, const wb2_weights* w, int skipna,
                          double* out_host);
 
+/* ---- host-streaming entries and the slab cache ----------------------------------
+ * Every *_host entry takes HOST base pointers (pinned memory reaches the PCIe
+ * rate; pageable memory works at the driver's staging rate), streams the 2-D
+ * slabs through two device staging buffers with the copies overlapped against
+ * the kernels, and returns after the result is in host memory.
+ *
+ * wb2_set_slab_cache(ctx, bytes) reserves `bytes` of HBM as an LRU cache of
+ * host slabs keyed by host address: the operands that repeat from chunk to
+ * chunk -- the truth slabs of truth.sel(time=valid_time) (evaluation.py:475)
+ * and the climatology slabs of the day-of-year lookup (metrics.py:398-404) --
+ * then cross PCIe once instead of once per chunk (the forecast is never
+ * cached).  The caller must not modify cached host arrays while the cache is
+ * enabled; bytes = 0 (the default) disables it and frees the arena.
+ * wb2_transfer_stats: which = 0 H2D bytes, 1 D2H bytes, 2 cache hits,
+ * 3 cache misses of the *_host entries since the last reset.                     */
+int wb2_set_slab_cache(wb2_ctx* ctx, size_t bytes);
+int64_t wb2_transfer_stats(const wb2_ctx* ctx, int which);
+int wb2_reset_transfer_stats(wb2_ctx* ctx);
+
+/* wb2_ens_metrics on host buffers (x, t host base pointers, out host
+ * [nfield][nregion][WB2_ENS_NSTAT]); truth slabs go through the slab cache.      */
+int wb2_ens_metrics_host(wb2_ctx* ctx, const void* x, const void* t, int dtype,
+                         int32_t nmember, int64_t member_stride, int64_t nfield,
+                         const int64_t* off_x, const int64_t* off_t,
+                         const wb2_weights* w, int skipna, double* out_host);
+
 /* ---- K2: ensemble metrics --------------------------------------------------
  * Replaces CRPS / CRPSSkill / CRPSSpread, EnsembleMeanMSE / RMSE,
  * EnsembleVariance / Stddev, DebiasedEnsembleMeanMSE .compute_chunk
@@ -357,6 +383,13 @@ int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* dst,
                             int64_t dst_field_stride, const wb2_csr* lon_w,
                             const wb2_csr* lat_w);
 
+/* wb2_regrid_conservative on host buffers: groups of fields in, regridded
+ * groups out (H2D, kernel and D2H of neighbouring groups overlap).             */
+int wb2_regrid_conservative_host(wb2_ctx* ctx, const float* src, float* dst,
+                                 int64_t nfield, int64_t src_field_stride,
+                                 int64_t dst_field_stride, const wb2_csr* lon_w,
+                                 const wb2_csr* lat_w);
+
 /* ---- K8: nearest-neighbour and bilinear regridding -----------------------------
  * wb2_regrid_gather replaces NearestRegridder.regrid_array
  * (regridding.py:231-247): dst[k] = src[indices[k]], `indices` host [ntarget]
@@ -410,6 +443,20 @@ int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield,
 int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
                               int32_t nrow, int32_t ncol, const double* scale,
                               float* out, int64_t nfield_out);
+
+/* wb2_zonal_spectrum / wb2_zonal_spectrum_latsum on host buffers.  x host
+ * [nfield][nrow][ncol] dense; out host, OVERWRITTEN: accumulate == 0:
+ * [nfield][nrow][ncol/2+1]; accumulate != 0: the sum over the fields of each
+ * slot, [nfield_out][nrow][ncol/2+1] (the accumulator stays in HBM, only the
+ * sum comes back); latsum: [nfield_out][ncol/2+1].                             */
+int wb2_zonal_spectrum_host(wb2_ctx* ctx, const float* x, int64_t nfield,
+                            int32_t nrow, int32_t ncol, const double* scale,
+                            float* out_host, int32_t accumulate,
+                            int64_t nfield_out);
+int wb2_zonal_spectrum_latsum_host(wb2_ctx* ctx, const float* x, int64_t nfield,
+                                   int32_t nrow, int32_t ncol,
+                                   const double* scale, float* out_host,
+                                   int64_t nfield_out);
 
 #ifdef __cplusplus
 }

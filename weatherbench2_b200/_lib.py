@@ -143,6 +143,23 @@ PROTOTYPES = {
     'wb2_zonal_spectrum_latsum': (C.c_int, [_P, _P, C.c_int64, C.c_int32,
                                             C.c_int32, C.POINTER(C.c_double),
                                             _P, C.c_int64]),
+    'wb2_set_slab_cache': (C.c_int, [_P, C.c_size_t]),
+    'wb2_transfer_stats': (C.c_int64, [_P, C.c_int]),
+    'wb2_reset_transfer_stats': (C.c_int, [_P]),
+    'wb2_ens_metrics_host': (C.c_int, [_P, _P, _P, C.c_int, C.c_int32,
+                                       C.c_int64, C.c_int64, _I64P, _I64P,
+                                       C.POINTER(Weights), C.c_int, _P]),
+    'wb2_regrid_conservative_host': (C.c_int, [_P, _P, _P, C.c_int64,
+                                               C.c_int64, C.c_int64,
+                                               C.POINTER(Csr),
+                                               C.POINTER(Csr)]),
+    'wb2_zonal_spectrum_host': (C.c_int, [_P, _P, C.c_int64, C.c_int32,
+                                          C.c_int32, C.POINTER(C.c_double), _P,
+                                          C.c_int32, C.c_int64]),
+    'wb2_zonal_spectrum_latsum_host': (C.c_int, [_P, _P, C.c_int64, C.c_int32,
+                                                 C.c_int32,
+                                                 C.POINTER(C.c_double), _P,
+                                                 C.c_int64]),
 }
 
 
@@ -183,7 +200,8 @@ _COMPUTE = frozenset(n for n in PROTOTYPES if n not in (
     'wb2_version', 'wb2_last_error', 'wb2_has_cuda', 'wb2_launch_count',
     'wb2_create', 'wb2_destroy', 'wb2_set_stream', 'wb2_get_stream',
     'wb2_synchronize', 'wb2_wait_stream', 'wb2_stream_wait', 'wb2_malloc',
-    'wb2_free', 'wb2_host_alloc', 'wb2_host_free'))
+    'wb2_free', 'wb2_host_alloc', 'wb2_host_free', 'wb2_set_slab_cache',
+    'wb2_transfer_stats', 'wb2_reset_transfer_stats'))
 
 
 def _torch_current_stream(device: int):
@@ -260,6 +278,7 @@ class Context:
     h = _P()
     check(self.lib.wb2_create(int(device), C.byref(h)))
     self.handle = h
+    self._slab_cache_bytes = 0
     self._closed = False
 
   def close(self):
@@ -322,6 +341,29 @@ class Context:
                                   out.nbytes))
     return out
 
+  # -- slab cache / transfer accounting of the *_host entries -------------------
+  def set_slab_cache(self, nbytes: int):
+    check(self.lib.wb2_set_slab_cache(self.handle, int(nbytes)))
+    self._slab_cache_bytes = int(nbytes)
+
+  def slab_cache(self, nbytes: Optional[int] = None):
+    """`with ctx.slab_cache(nbytes):` -- keeps the truth / climatology slabs of
+    the *_host entries resident in HBM inside the block (LRU, keyed by host
+    address; the host arrays must not change meanwhile) and drops them on
+    exit.  Default size: 30 % of the free device memory, at most 48 GiB.
+    Re-entrant: an enclosing scope's cache is kept."""
+    return _SlabCacheScope(self, nbytes)
+
+  def transfer_stats(self) -> dict:
+    f = self.lib.wb2_transfer_stats
+    return {'h2d_bytes': int(f(self.handle, 0)),
+            'd2h_bytes': int(f(self.handle, 1)),
+            'cache_hits': int(f(self.handle, 2)),
+            'cache_misses': int(f(self.handle, 3))}
+
+  def reset_transfer_stats(self):
+    check(self.lib.wb2_reset_transfer_stats(self.handle))
+
   # -- K1 ---------------------------------------------------------------------
   def det_metrics(self, f: int, t: int, c: Optional[int], dtype: int,
                   off_f: np.ndarray, off_t: np.ndarray,
@@ -352,6 +394,16 @@ class Context:
     w = weights.as_struct()
     check(self.lib.wb2_ens_metrics(
         self.handle, _P(x), _P(t), dtype, int(nmember), int(member_stride),
+        int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
+        C.byref(w), int(bool(skipna)), _P(out)))
+
+  def ens_metrics_host(self, x: int, t: int, nmember: int, member_stride: int,
+                       off_x: np.ndarray, off_t: np.ndarray,
+                       weights: 'WeightSpec', skipna: bool, out: int):
+    """x / t / out are HOST addresses (wb2_ens_metrics_host)."""
+    w = weights.as_struct()
+    check(self.lib.wb2_ens_metrics_host(
+        self.handle, _P(x), _P(t), F32, int(nmember), int(member_stride),
         int(off_x.size), _as_ptr(off_x, C.c_int64), _as_ptr(off_t, C.c_int64),
         C.byref(w), int(bool(skipna)), _P(out)))
 
@@ -454,6 +506,15 @@ class Context:
         self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
         int(dst_stride), C.byref(a), C.byref(b)))
 
+  def regrid_conservative_host(self, src: int, dst: int, nfield: int,
+                               src_stride: int, dst_stride: int,
+                               lon_w: 'CsrSpec', lat_w: 'CsrSpec'):
+    """src / dst are HOST addresses (wb2_regrid_conservative_host)."""
+    a, b = lon_w.as_struct(), lat_w.as_struct()
+    check(self.lib.wb2_regrid_conservative_host(
+        self.handle, _P(src), _P(dst), int(nfield), int(src_stride),
+        int(dst_stride), C.byref(a), C.byref(b)))
+
   # -- derived variables -------------------------------------------------------
   def wind_speed(self, u: int, v: int, out: int, n: int):
     check(self.lib.wb2_wind_speed(self.handle, _P(u), _P(v), _P(out), int(n)))
@@ -525,6 +586,24 @@ class Context:
         int(nfield_out)))
 
 
+  def zonal_spectrum_host(self, x: int, nfield: int, nrow: int, ncol: int,
+                          scale: np.ndarray, out: int, accumulate: bool = False,
+                          nfield_out: int = 0):
+    """x / out are HOST addresses (wb2_zonal_spectrum_host)."""
+    scale = np.ascontiguousarray(scale, dtype=np.float64)
+    check(self.lib.wb2_zonal_spectrum_host(
+        self.handle, _P(x), int(nfield), int(nrow), int(ncol),
+        _as_ptr(scale, C.c_double), _P(out), int(bool(accumulate)),
+        int(nfield_out)))
+
+  def zonal_spectrum_latsum_host(self, x: int, nfield: int, nrow: int,
+                                 ncol: int, scale: np.ndarray, out: int,
+                                 nfield_out: int):
+    scale = np.ascontiguousarray(scale, dtype=np.float64)
+    check(self.lib.wb2_zonal_spectrum_latsum_host(
+        self.handle, _P(x), int(nfield), int(nrow), int(ncol),
+        _as_ptr(scale, C.c_double), _P(out), int(nfield_out)))
+
   def zonal_spectrum_latsum(self, x: int, nfield: int, nrow: int, ncol: int,
                             scale: np.ndarray, out: int, nfield_out: int):
     """out[slot][k] = sum over the slot's fields and over rows of
@@ -533,6 +612,44 @@ class Context:
     check(self.lib.wb2_zonal_spectrum_latsum(
         self.handle, _P(x), int(nfield), int(nrow), int(ncol),
         _as_ptr(scale, C.c_double), _P(out), int(nfield_out)))
+
+
+class _SlabCacheScope:
+  """Context manager behind Context.slab_cache()."""
+
+  def __init__(self, ctx: 'Context', nbytes: Optional[int]):
+    self.ctx, self.nbytes, self.owner = ctx, nbytes, False
+
+  def __enter__(self):
+    ctx = self.ctx
+    if getattr(ctx, '_slab_cache_bytes', 0) > 0:
+      return ctx  # an enclosing scope already holds a cache
+    nbytes = self.nbytes
+    if nbytes is None:
+      nbytes = default_slab_cache_bytes(ctx.device)
+    if nbytes > 0:
+      ctx.set_slab_cache(nbytes)
+      self.owner = True
+    return ctx
+
+  def __exit__(self, *exc):
+    if self.owner:
+      self.ctx.set_slab_cache(0)
+    return False
+
+
+def default_slab_cache_bytes(device: int) -> int:
+  """30 % of the free device memory, capped at 48 GiB (WB2_SLAB_CACHE_MB
+  overrides; 0 disables)."""
+  env = os.environ.get('WB2_SLAB_CACHE_MB')
+  if env is not None:
+    return int(env) << 20
+  try:
+    import torch  # pylint: disable=import-outside-toplevel
+    free, _ = torch.cuda.mem_get_info(device)
+  except Exception:  # pylint: disable=broad-except
+    free = 16 << 30
+  return int(min(0.3 * free, 48 << 30))
 
 
 class WeightSpec:

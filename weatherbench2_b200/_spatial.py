@@ -413,10 +413,40 @@ def split_member_dim(op: Operand, ens_dim: str):
   return out, int(m), int(stride)
 
 
+def _upload_gathered(ctx: _lib.Context, op: Operand, staged: list) -> Operand:
+  """Uploads ONLY the slabs a gathered host operand references (a by-init truth
+  gather or a day-of-year climatology lookup addresses a few slabs of a long
+  record: uploading the whole backing array, per variable and chunk, is what
+  the round-1 review flagged), packed contiguously, and re-addresses the
+  operand through one explicit offset term."""
+  dims, shape = op.outer_dims, op.outer_shape
+  table = offset_table(op, dims, shape)
+  uniq, inv = np.unique(table, return_inverse=True)
+  slab = (op.nrow - 1) * op.row_stride + op.ncol
+  pad = (slab + 63) // 64 * 64
+  es = op.itemsize
+  packed = np.empty((uniq.size, pad), dtype=op.dtype)
+  for i, off in enumerate(uniq):
+    src = np.ctypeslib.as_array(
+        (np.ctypeslib.ctypes.c_char * (slab * es)).from_address(
+            op.addr + int(off) * es)).view(op.dtype)
+    packed[i, :slab] = src
+  dptr = ctx.to_device(packed)
+  staged.append(dptr)
+  out = dataclasses.replace(op, addr=dptr, on_device=True)
+  out.gather_terms = [(tuple(dims),
+                       (inv.astype(np.int64) * pad).reshape(shape))]
+  return out
+
+
 def _to_device_operand(ctx: _lib.Context, op: Operand, staged: list) -> Operand:
-  """Uploads a host operand's backing array (same strides) to the device."""
+  """Uploads a host operand to the device: the smallest contiguous span of its
+  backing array (same strides), or, for a gathered operand, only the slabs it
+  references."""
   if op.on_device:
     return op
+  if getattr(op, 'gather_terms', None) is not None:
+    return _upload_gathered(ctx, op, staged)
   arr = op.data
   base = arr
   while isinstance(base, np.ndarray) and base.base is not None and isinstance(
@@ -443,13 +473,18 @@ def run_ens_metrics(ctx: _lib.Context, x_ops: Sequence[Operand],
   """Runs K2 for variables sharing layout / grid.  Returns (stats, dims,
   shapes, M): stats[v] has shape outer_shape[v] + (len(regions), ENS_NSTAT)."""
   staged: list = []
+  # all-host float32 operands: stream member / truth slabs through the staging
+  # buffers (wb2_ens_metrics_host; truth slabs go through the slab cache)
+  host = all(not o.on_device and o.dtype == np.float32
+             for o in list(x_ops) + list(t_ops))
   try:
     xs, ts, ms, strides = [], [], [], []
     for xo, to in zip(x_ops, t_ops):
       if ens_dim in to.outer_dims:
         raise ValueError(f'truth must not have the {ens_dim!r} dimension')
-      xo = _to_device_operand(ctx, xo, staged)
-      to = _to_device_operand(ctx, to, staged)
+      if not host:
+        xo = _to_device_operand(ctx, xo, staged)
+        to = _to_device_operand(ctx, to, staged)
       xo, m, st = split_member_dim(xo, ens_dim)
       xs.append(xo)
       ts.append(to)
@@ -474,6 +509,12 @@ def run_ens_metrics(ctx: _lib.Context, x_ops: Sequence[Operand],
       nfield = off_x.size
       res = np.empty((nfield, nreg, _lib.ENS_NSTAT), dtype=np.float64)
       for ids, spec in groups:
+        if host:
+          part = np.empty((nfield, len(ids), _lib.ENS_NSTAT), np.float64)
+          ctx.ens_metrics_host(base, base, m, st, off_x, off_t, spec, skipna,
+                               part.ctypes.data)
+          res[:, ids, :] = part
+          continue
         out_dev = ctx.malloc(nfield * len(ids) * _lib.ENS_NSTAT * 8)
         try:
           ctx.ens_metrics(base, base, _lib.F32, m, st, off_x, off_t, spec,

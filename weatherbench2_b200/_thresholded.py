@@ -68,7 +68,9 @@ def _stats_to_dataset(res: dict, slot: int, quantile_coord, sum_quantile: bool,
     val = m._ratio(st[..., slot], st[..., 4 + slot])  # pylint: disable=protected-access
     val = np.moveaxis(val, -1, 0)  # quantile first
     if sum_quantile:
-      out[name] = xl.DataArray(val.sum(axis=0), dims, coords, name)
+      # xarray's `.sum("quantile")` (metrics.py:1158, 1866) skips NaN terms
+      # (skipna defaults to True for float data)
+      out[name] = xl.DataArray(np.nansum(val, axis=0), dims, coords, name)
     elif quantile_coord is None:
       out[name] = xl.DataArray(val[0], dims, coords, name)
     else:
@@ -323,7 +325,11 @@ class _SpatialEnsembleThresholdMetric(_EnsembleThresholdMetric):
       coords = m._map_coords(dims, f_da, t_da)  # pylint: disable=protected-access
       coords.pop(self.ensemble_dim, None)
       if self._SUM:  # metrics.py:1891 `.sum("quantile")`
-        out[name] = xl.DataArray(maps.sum(0), dims, coords, name)
+        if xl._is_torch(maps):  # pylint: disable=protected-access
+          total = maps.nansum(0)
+        else:
+          total = np.nansum(maps, axis=0)
+        out[name] = xl.DataArray(total, dims, coords, name)
       else:
         coords['quantile'] = _quantile_coords(thresholds)
         out[name] = xl.DataArray(maps, ('quantile',) + tuple(dims), coords,

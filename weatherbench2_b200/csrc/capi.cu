@@ -135,6 +135,7 @@ int wb2_destroy(wb2_ctx* c) {
     if (c->stage_copied[i]) cudaEventDestroy(c->stage_copied[i]);
     if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
   }
+  slab_cache_destroy(c);
   if (c->order_in) cudaEventDestroy(c->order_in);
   if (c->order_out) cudaEventDestroy(c->order_out);
   if (c->d_out_tmp) cudaFree(c->d_out_tmp);

@@ -81,6 +81,12 @@ struct wb2_ctx {
   // cross-stream ordering with a caller's stream (wb2_wait_stream / wb2_stream_wait)
   cudaEvent_t order_in = nullptr;
   cudaEvent_t order_out = nullptr;
+  // device-resident LRU cache of host slabs (host_stream.cu); 0 = disabled
+  void* slab_cache = nullptr;
+  size_t slab_cache_capacity = 0;
+  // transfer accounting of the *_host entries (wb2_transfer_stats)
+  int64_t stat_h2d_bytes = 0, stat_d2h_bytes = 0;
+  int64_t stat_cache_hits = 0, stat_cache_misses = 0;
 };
 
 namespace wb2 {
@@ -127,6 +133,7 @@ struct DeviceGuard {
 };
 
 int validate_weights(const wb2_weights* w);
+void slab_cache_destroy(wb2_ctx* ctx);  // host_stream.cu
 
 // ens_big.cu: ensembles of more than 64 members (rank by counting).
 int ens_metrics_big(wb2_ctx* ctx, const float* x, const float* t, int32_t nmember,

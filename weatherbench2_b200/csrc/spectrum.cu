@@ -481,23 +481,21 @@ int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
 
 // out[slot][k] = sum_row spec[slot][row][k]   (rows already carry their weights)
 __global__ void latsum_rows_kernel(const float* __restrict__ spec, float* __restrict__ out,
-                                   int64_t nslot, int nrow, int nk) {
+                                   int64_t nslot, int nrow, int nk, int accumulate) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= nslot * nk) return;
   const int64_t slot = i / nk;
   const int k = static_cast<int>(i - slot * nk);
   float s = 0.f;
   for (int r = 0; r < nrow; ++r) s += spec[(slot * nrow + r) * int64_t(nk) + k];
-  out[i] = s;
+  out[i] = accumulate ? out[i] + s : s;
 }
 
-}  // namespace wb2
-
-using namespace wb2;
-
-extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
-                                         int32_t nrow, int32_t ncol, const double* scale,
-                                         float* out, int64_t nfield_out) {
+// wb2_zonal_spectrum_latsum; accumulate != 0 adds to `out` (the host-streaming
+// entry sums groups of time steps this way).
+int spectrum_latsum_impl(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
+                         int32_t ncol, const double* scale, float* out, int64_t nfield_out,
+                         int accumulate) {
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nrow > 0 && ncol > 1, "bad grid %d x %d", nrow, ncol);
   WB2_REQUIRE(nfield >= 0, "nfield < 0");
@@ -507,7 +505,8 @@ extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t n
               "nfield (%lld) must be a multiple of nfield_out (%lld)",
               static_cast<long long>(nfield), static_cast<long long>(nfield_out));
   DeviceGuard guard(ctx->device);
-  const int prc = spectrum_pfa_try(ctx, x, nfield, nrow, ncol, scale, out, 2, nfield_out);
+  const int prc = spectrum_pfa_try(ctx, x, nfield, nrow, ncol, scale, out, accumulate ? 3 : 2,
+                                   nfield_out);
   if (prc != 0) return prc < 0 ? prc : WB2_OK;
   // other row lengths / unaligned data: per-row spectra (time-summed) into
   // scratch, then the row sum
@@ -526,10 +525,20 @@ extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t n
   WB2_TRY(wb2_zonal_spectrum(ctx, x, nfield, nrow, ncol, scale, spec, 1, nfield_out));
   const int64_t n = nfield_out * nk;
   latsum_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
-      spec, out, nfield_out, nrow, nk);
+      spec, out, nfield_out, nrow, nk, accumulate);
   WB2_CUDA_TRY(cudaGetLastError());
   ctx->launches += 1;
   return WB2_OK;
+}
+
+}  // namespace wb2
+
+using namespace wb2;
+
+extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
+                                         int32_t nrow, int32_t ncol, const double* scale,
+                                         float* out, int64_t nfield_out) {
+  return spectrum_latsum_impl(ctx, x, nfield, nrow, ncol, scale, out, nfield_out, 0);
 }
 
 extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,

@@ -604,6 +604,8 @@ static void build_tables(std::vector<float4>* twn, std::vector<int4>* ctask) {
 template <class P>
 static int launch(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
                   const double* scale, float* out, int mode, int64_t nslot) {
+  const int latsum_accumulate = mode == 3;  // mode 3 = mode 2 adding to `out`
+  if (mode == 3) mode = 2;
   std::vector<float4> twn;
   std::vector<int4> ctask;
   build_tables<P>(&twn, &ctask);
@@ -662,7 +664,7 @@ static int launch(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
   if (mode == 2) {
     const int64_t n = nslot * P::NK;
     latsum_finalize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
-        p.out, out, nslot, p.nchunk, P::NK, 0);
+        p.out, out, nslot, p.nchunk, P::NK, latsum_accumulate);
     WB2_CUDA_TRY(cudaGetLastError());
     ctx->launches += 1;
   }
@@ -675,8 +677,9 @@ static int launch(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
 // Returns 1 when the prime-factor kernel handled the call, 0 when the shape /
 // alignment is not eligible (the caller falls back), < 0 on error.
 //   mode 0: out[field][row][k] = S;   mode 1: out[slot][row][k] += sum_time S;
-//   mode 2: out[slot][k] = sum_time sum_row scale[row] S / circumference-free:
-//           `scale` already holds circumference * row weight.
+//   mode 2: out[slot][k] = sum_time sum_row scale[row] * S-without-circumference
+//           (`scale` already holds circumference * row weight);  mode 3: same,
+//           added to `out`.
 int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow, int32_t ncol,
                      const double* scale, float* out, int mode, int64_t nslot) {
   const char* force = getenv("WB2_SPECTRUM_PATH");

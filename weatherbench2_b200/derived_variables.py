@@ -119,17 +119,14 @@ class ZonalEnergySpectrum(DerivedVariable):
       ctx.synchronize()
       values = out
     else:
+      # host data: streamed through double-buffered staging; with a time sum
+      # the accumulator stays in HBM and only the sum comes back
       x = np.ascontiguousarray(np.asarray(data), dtype=np.float32)
-      src = ctx.to_device(x)
-      dst = ctx.malloc(max(1, nout * nlat * nk * 4))
-      try:
-        ctx.lib.wb2_memset(ctx.handle, dst, 0, nout * nlat * nk * 4)
-        ctx.zonal_spectrum(src, nfield, nlat, nlon, scale, dst,
-                           time_sum_dim is not None, nout)
-        values = ctx.from_device(dst, res_shape, np.float32)
-      finally:
-        ctx.free(src)
-        ctx.free(dst)
+      values = np.zeros(res_shape, dtype=np.float32)
+      if nfield:
+        ctx.zonal_spectrum_host(x.ctypes.data, nfield, nlat, nlon, scale,
+                                values.ctypes.data, time_sum_dim is not None,
+                                nout)
     out_outer = outer[1:] if time_sum_dim is not None else outer
     dims = out_outer + ('latitude', 'zonal_wavenumber')
     base_frequency = np.fft.rfftfreq(nlon)  # derived_variables.py:614

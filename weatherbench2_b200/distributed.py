@@ -141,6 +141,13 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
     rank, world = dist.get_rank(group), dist.get_world_size(group)
   else:
     rank, world = 0, 1
+  cache_scope = None
+  if loop_fn is None:
+    # product path: keep the truth / climatology slabs that repeat from chunk
+    # to chunk resident in HBM for the duration of the sweep (host inputs only;
+    # the datasets are not modified while we hold them)
+    from weatherbench2_b200 import _lib  # pylint: disable=import-outside-toplevel
+    cache_scope = _lib.default_context().slab_cache()
   loop_fn = loop_fn or evaluation._metric_and_region_loop  # pylint: disable=protected-access
   if select_truth is None:
     select_truth = (evaluation.select_truth_at_valid_time
@@ -148,11 +155,13 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   n = forecast.sizes[chunk_dim]
   nchunks = (n + chunk_size - 1) // chunk_size
   acc = TimeMeanAccumulator(chunk_dim, skipna)
-  for ci in shard_indices(nchunks, rank, world):
-    sl = slice(int(ci) * chunk_size, min(n, (int(ci) + 1) * chunk_size))
-    fc = forecast.isel({chunk_dim: sl})
-    tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
-    acc.add(loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True))
+  import contextlib  # pylint: disable=import-outside-toplevel
+  with (cache_scope if cache_scope is not None else contextlib.nullcontext()):
+    for ci in shard_indices(nchunks, rank, world):
+      sl = slice(int(ci) * chunk_size, min(n, (int(ci) + 1) * chunk_size))
+      fc = forecast.isel({chunk_dim: sl})
+      tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
+      acc.add(loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True))
   if not acc.sums:
     # a rank without chunks still has to take part in the collective with the
     # right payload shape: evaluate nothing, contribute zeros

@@ -155,6 +155,16 @@ def open_forecast_and_truth_datasets(data_config: config.Data,
   for coord_name in ('latitude', 'longitude'):  # evaluation.py:49-61
     np.testing.assert_allclose(forecast[coord_name].values,
                                obs[coord_name].values, atol=1e-3)
+  # _ensure_aligned_grid (evaluation.py:49-61): after the closeness check the
+  # forecast's coordinates REPLACE the others', so that float32 / float64
+  # coordinate labels cannot turn the later label joins into gathers
+  grid = {k: forecast[k].values for k in ('latitude', 'longitude')}
+  obs = obs.assign_coords(grid)
+  if climatology is not None:
+    for coord_name in ('latitude', 'longitude'):
+      np.testing.assert_allclose(forecast[coord_name].values,
+                                 climatology[coord_name].values, atol=1e-3)
+    climatology = climatology.assign_coords(grid)
   forecast = apply_time_conventions(forecast, data_config.by_init)
 
   variables = list(sel.variables)

@@ -5,7 +5,9 @@
 The weight matrices are built here with the reference's formulas (cell-overlap
 areas along latitude, periodic interval overlaps along longitude) in float32,
 the precision JAX uses by default, and handed to the kernel in CSR form.
-Nearest / bilinear regridders (regridding.py:212-294) are out of scope.
+Nearest / bilinear regridders (regridding.py:212-294): _regrid_interp.py.
+NumPy inputs are streamed through double-buffered device staging
+(wb2_regrid_conservative_host); CUDA tensors stay on the device.
 """
 from __future__ import annotations
 
@@ -187,6 +189,10 @@ class Regridder:
       return out
     x = np.ascontiguousarray(np.asarray(field), dtype=np.float32)
     nt = self.target.shape[0] * self.target.shape[1]
+    out = np.empty(tshape, dtype=np.float32)
+    if nfield and self.regrid_host(ctx, x.ctypes.data, out.ctypes.data,
+                                   nfield):
+      return out  # streamed: H2D, kernel and D2H of neighbouring groups overlap
     src = ctx.to_device(x)
     dst = ctx.malloc(max(1, nfield * nt * 4))
     try:
@@ -195,6 +201,13 @@ class Regridder:
     finally:
       ctx.free(src)
       ctx.free(dst)
+
+  def regrid_host(self, ctx: _lib.Context, src_ptr: int, dst_ptr: int,
+                  nfield: int) -> bool:
+    """Host-pointer entry (double-buffered streaming); False = not available
+    for this regridder (the caller stages whole arrays instead)."""
+    del ctx, src_ptr, dst_ptr, nfield
+    return False
 
   def regrid_dataset(self, dataset):
     """Regrid a Dataset from source to target (regridding.py:193-209)."""
@@ -250,6 +263,15 @@ class ConservativeRegridder(Regridder):
     nt = self.target.shape[0] * self.target.shape[1]
     ctx.regrid_conservative(src_ptr, dst_ptr, nfield, src_stride or ns,
                             dst_stride or nt, lon_w, lat_w)
+
+  def regrid_host(self, ctx: _lib.Context, src_ptr: int, dst_ptr: int,
+                  nfield: int) -> bool:
+    lon_w, lat_w = self._weights
+    ns = self.source.shape[0] * self.source.shape[1]
+    nt = self.target.shape[0] * self.target.shape[1]
+    ctx.regrid_conservative_host(src_ptr, dst_ptr, nfield, ns, nt, lon_w,
+                                 lat_w)
+    return True
 
 
 # Nearest / bilinear regridders live in _regrid_interp.py (they need Regridder).

@@ -1001,6 +1001,15 @@ def align_inner(a: DataArray, b: DataArray):
     ca, cb = a.coords[d].values, b.coords[d].values
     if ca.shape == cb.shape and np.array_equal(ca, cb):
       continue
+    if d in ('latitude', 'longitude'):
+      # the kernels address whole (lat, lon) slabs: a label join along a
+      # spatial dimension cannot be folded into an offset table, and silently
+      # falling back to positional alignment would be wrong (the reference's
+      # _ensure_aligned_grid makes the grids identical up front)
+      raise ValueError(
+          f'{d} coordinates of the two operands differ; align the grids first '
+          '(evaluation.open_forecast_and_truth_datasets assigns the '
+          "forecast's coordinates like the reference's _ensure_aligned_grid)")
     keep = np.isin(ca, cb)
     labels = ca[keep]
     maps_a[d] = ((d,), np.nonzero(keep)[0])
