@@ -515,19 +515,28 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
       if (c_on) {
         float* ta = tile + (2 * c_g) * NK;
         float* tb = ta + NK;
+        // modes 0 / 1: the per-row factor is applied here, so that the copy-out
+        // below is a flat, unrolled add (mode 2 applied it per item already)
+        float sa = 1.f, sb = 1.f;
+        if (MODE != 2) {
+          const int row = 2 * (G * cur.gi + c_g);
+          sa = __ldg(p.scale + row);
+          sb = __ldg(p.scale + row + 1);
+        }
 #pragma unroll
         for (int kC = 0; kC < RC; ++kC) {
           int pbin = c_k0 + (kC * P::EC) % N2;
           pbin = pbin >= N2 ? pbin - N2 : pbin;
           const bool va = !c_self || kC <= (RC - kC) % RC;
           const bool vb = va && (2 * pbin != N2);
+          const float h0 = pbin == 0 ? 0.5f : 1.f;  // c_k = 1 for the zonal mean
           if (va) {
-            ta[pbin] = lo2(acc_a[kC]);
-            tb[pbin] = hi2(acc_a[kC]);
+            ta[pbin] = lo2(acc_a[kC]) * (sa * h0);
+            tb[pbin] = hi2(acc_a[kC]) * (sb * h0);
           }
           if (vb) {
-            ta[N2 - pbin] = lo2(acc_b[kC]);
-            tb[N2 - pbin] = hi2(acc_b[kC]);
+            ta[N2 - pbin] = lo2(acc_b[kC]) * sa;
+            tb[N2 - pbin] = hi2(acc_b[kC]) * sb;
           }
           acc_a[kC] = acc_b[kC] = 0ull;
         }
@@ -540,17 +549,27 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
           float s = 0.f;
 #pragma unroll
           for (int r = 0; r < 2 * G; ++r) s += tile[r * NK + k];
-          o[k] = k == 0 ? 0.5f * s : s;
+          o[k] = s;
         }
       } else {
+        // the rows of a group are contiguous in `out`: one flat range; loads of
+        // the read-modify-write are issued kU at a time (the un-unrolled loop
+        // held a third of the kernel's stall samples on the first FFMA)
         const int row0 = 2 * G * cur.gi;
-        const int nr = min(2 * G, p.nrow - row0);
+        const int n = min(2 * G, p.nrow - row0) * NK;
         float* o = p.out + (cur.slot * p.nrow + row0) * int64_t(NK);
-        for (int r = 0; r < nr; ++r) {
-          const float sc = __ldg(p.scale + row0 + r);
-          for (int k = tid; k < NK; k += NT) {
-            const float v = tile[r * NK + k] * (k == 0 ? 0.5f * sc : sc);
-            o[r * NK + k] = MODE == 1 ? o[r * NK + k] + v : v;
+        constexpr int kU = 6;
+        for (int i0 = tid; i0 < n; i0 += kU * NT) {
+          float v[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int i = i0 + u * NT;
+            v[u] = (MODE == 1 && i < n) ? o[i] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int i = i0 + u * NT;
+            if (i < n) o[i] = v[u] + tile[i];
           }
         }
       }

@@ -122,7 +122,9 @@ class ZonalEnergySpectrum(DerivedVariable):
       # host data: streamed through double-buffered staging; with a time sum
       # the accumulator stays in HBM and only the sum comes back
       x = np.ascontiguousarray(np.asarray(data), dtype=np.float32)
-      values = np.zeros(res_shape, dtype=np.float32)
+      values = ctx.pinned_result(res_shape, np.float32)  # overwritten below
+      if not nfield:
+        values[...] = 0
       if nfield:
         ctx.zonal_spectrum_host(x.ctypes.data, nfield, nlat, nlon, scale,
                                 values.ctypes.data, time_sum_dim is not None,

@@ -189,7 +189,7 @@ class Regridder:
       return out
     x = np.ascontiguousarray(np.asarray(field), dtype=np.float32)
     nt = self.target.shape[0] * self.target.shape[1]
-    out = np.empty(tshape, dtype=np.float32)
+    out = ctx.pinned_result(tshape, np.float32)
     if nfield and self.regrid_host(ctx, x.ctypes.data, out.ctypes.data,
                                    nfield):
       return out  # streamed: H2D, kernel and D2H of neighbouring groups overlap
