@@ -185,6 +185,11 @@ static int check_csr(const wb2_csr* m, const char* name) {
   return WB2_OK;
 }
 
+// regrid_tma.cu: TMA-staged persistent variant (1 = handled, 0 = not eligible)
+int regrid_tma_try(wb2_ctx* ctx, const float* src, float* dst, int64_t nfield,
+                   int64_t src_field_stride, int64_t dst_field_stride, const wb2_csr* lon_w,
+                   const wb2_csr* lat_w);
+
 }  // namespace wb2
 
 using namespace wb2;
@@ -209,6 +214,11 @@ extern "C" int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* ds
     return WB2_EUNSUPPORTED;
   }
   DeviceGuard guard(ctx->device);
+  {
+    const int trc = regrid_tma_try(ctx, src, dst, nfield, src_field_stride, dst_field_stride,
+                                   lon_w, lat_w);
+    if (trc != 0) return trc < 0 ? trc : WB2_OK;
+  }
 
   // per-group union of source rows + dense G-wide weight table (host, tiny)
   const int nlon_t = lon_w->n_tgt;
