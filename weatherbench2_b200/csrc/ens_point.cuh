@@ -6,13 +6,74 @@
 
 namespace wb2 {
 
-#define CE(a, b)                          \
-  {                                       \
-    const float lo_ = fminf(v[a], v[b]);  \
-    const float hi_ = fmaxf(v[a], v[b]);  \
-    v[a] = lo_;                           \
-    v[b] = hi_;                           \
-  }
+typedef unsigned long long u64x2f;  // two packed float32 (PTX .f32x2)
+
+__device__ __forceinline__ u64x2f pk2f(float lo, float hi) {
+  u64x2f r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2f(u64x2f v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64x2f add2f(u64x2f a, u64x2f b) {
+  u64x2f r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64x2f sub2f(u64x2f a, u64x2f b) {
+  u64x2f r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64x2f fma2f(u64x2f a, u64x2f b, u64x2f c) {
+  u64x2f r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// compare-exchange of one element (scalar members of one grid point)
+__device__ __forceinline__ void ce_any(float& a, float& b) {
+  const float lo_ = fminf(a, b);
+  const float hi_ = fmaxf(a, b);
+  a = lo_;
+  b = hi_;
+}
+// compare-exchange of the SAME comparator on two adjacent grid points held as
+// one packed pair per member (ens_pair_kernel): the two minima are scalar FMNMX
+// (ALU pipe), the two maxima come from hi = (a + b) - lo as two FADD2 (FMA
+// pipe) -- every comparator of the network is pipe-balanced, and the pairs need
+// no register shuffling because they are loaded as pairs (LDG.64).  Inexact by
+// one rounding of the pair sum: only used on mean-removed members.
+__device__ __forceinline__ void ce_any(u64x2f& a, u64x2f& b) {
+  float a0, a1, b0, b1;
+  unpk2f(a, a0, a1);
+  unpk2f(b, b0, b1);
+  const u64x2f lo = pk2f(fminf(a0, b0), fminf(a1, b1));
+  b = sub2f(add2f(a, b), lo);
+  a = lo;
+}
+// exact variant of the pair comparator: maxima on the ALU pipe too
+__device__ __forceinline__ void ce_any_minmax(u64x2f& a, u64x2f& b) {
+  float a0, a1, b0, b1;
+  unpk2f(a, a0, a1);
+  unpk2f(b, b0, b1);
+  a = pk2f(fminf(a0, b0), fminf(a1, b1));
+  b = pk2f(fmaxf(a0, b0), fmaxf(a1, b1));
+}
+// Comparator K of the generated networks.  Scalar members: always min / max.
+// Packed pairs: two of three comparators take the FADD2 form, every third one
+// min / max, which splits the work evenly between the FMA pipe (that also does
+// the moment sums) and the ALU pipe (ncu, ens_pair_kernel<50>: FMA 60 % / ALU
+// 48 % busy with the FADD2 form everywhere).
+template <int K>
+__device__ __forceinline__ void ce_sel(float& a, float& b) { ce_any(a, b); }
+template <int K>
+__device__ __forceinline__ void ce_sel(u64x2f& a, u64x2f& b) {
+  if (K % 3 == 0) ce_any_minmax(a, b);
+  else ce_any(a, b);
+}
+#define CE(a, b) ce_sel<__COUNTER__>(v[a], v[b]);
 // Twin compare-exchange on two aligned register pairs (v[a], v[a+1]) and
 // (v[b], v[b+1]): the minima still cost one FMNMX each (ALU pipe, one warp
 // instruction per 2 cycles per SM sub-partition), but the maxima come from
