@@ -283,6 +283,27 @@ int wb2_seeps_maps(wb2_ctx* ctx, const float* f, const float* t, const float* we
 int wb2_wind_speed(wb2_ctx* ctx, const float* u, const float* v, float* out,
                    int64_t n);
 
+/* wb2_ens_mean replaces the ensemble-mean pipeline of
+ * scripts/compute_ensemble_mean.py:110-141 (xbeam.Mean(realization, skipna)):
+ * out[field][cell] = mean_m x[off_x[field] + m * member_stride + cell], float32;
+ * skipna: mean over the non-NaN members (NaN when there is none).  Device
+ * pointers; `slab` = cells per field (contiguous); out [nfield][slab].  The mean
+ * stays in HBM for K1 (ensemble-mean RMSE / ACC) -- no host round trip.        */
+int wb2_ens_mean(wb2_ctx* ctx, const float* x, int32_t nmember,
+                 int64_t member_stride, int64_t nfield, const int64_t* off_x,
+                 int64_t slab, int skipna, float* out);
+
+/* wb2_spectrum_interp replaces interpolate_spectral_frequencies
+ * (derived_variables.py:629-682) on the output of wb2_zonal_spectrum: row `lat`
+ * of a spectrum lives on the increasing frequencies freq_table[lat][k] (host
+ * [nrow][nk] float64, the `frequency` coordinate of the reference's result);
+ * every row is interpolated linearly to the common `freqs` (host [nfreq],
+ * float64), NaN outside the row's range like xarray's .interp.
+ *   spec device [nfield][nrow][nk] float32;  out device [nfield][nrow][nfreq]    */
+int wb2_spectrum_interp(wb2_ctx* ctx, const float* spec, int64_t nfield,
+                        int32_t nrow, int32_t nk, const double* freq_table,
+                        int32_t nfreq, const double* freqs, float* out);
+
 /* ---- K10: rank histogram ---------------------------------------------------------
  * Replaces RankHistogram.compute_chunk (metrics.py:1894-2042) and the time mean
  * of EnsembleMetric.compute: rank of the truth among the members (NaN last),

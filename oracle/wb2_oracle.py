@@ -699,6 +699,60 @@ def zonal_energy_spectrum(x, dims, lat, lon):
   return spectrum, out_dims, frequency, wavelength
 
 
+def zonal_energy_spectrum_latitude_mean(x, dims, lat, lon, lat_slice=None):
+  """The north star's "weighted meridional reduction" after the rFFT, defined on
+  the reference's own pieces: the get_lat_weights-weighted (metrics.py:40-60)
+  latitude mean of ZonalEnergySpectrum.compute (derived_variables.py:592-626),
+  optionally over a label-inclusive latitude band.  Returns (result, dims)."""
+  spec, sd, _, _ = zonal_energy_spectrum(x, dims, lat, lon)
+  lat = np.asarray(lat)
+  w = get_lat_weights(lat)
+  if lat_slice is not None:
+    lo = -np.inf if lat_slice.start is None else lat_slice.start
+    hi = np.inf if lat_slice.stop is None else lat_slice.stop
+    w = w * ((lat >= lo) & (lat <= hi))
+  ax = sd.index(LAT)
+  shape = [1] * spec.ndim
+  shape[ax] = lat.size
+  out = (spec * w.reshape(shape)).sum(axis=ax) / w.sum()
+  return out, tuple(d for d in sd if d != LAT)
+
+
+def interpolate_spectral_frequencies(spectrum, frequency, frequencies=None):
+  """derived_variables.py:629-682 with its third-party call made directly:
+  xarray's DataArray.interp(method='linear') is scipy.interpolate.interp1d(
+  kind='linear', bounds_error=False, fill_value=nan) along the coordinate.
+  spectrum: (..., latitude, wavenumber); frequency: (wavenumber, latitude).
+  Returns (result (..., latitude, frequency), frequencies)."""
+  from scipy import interpolate  # pylint: disable=import-outside-toplevel
+  spectrum = np.asarray(spectrum)
+  frequency = np.asarray(frequency, dtype=np.float64)
+  nk, nlat = frequency.shape
+  if frequencies is None:  # :658-664
+    freq_min = frequency.max(axis=1).min()
+    freq_max = frequency.min(axis=1).max()
+    frequencies = np.linspace(freq_min, freq_max, num=nk)
+  frequencies = np.asarray(frequencies, dtype=np.float64)
+  out = np.empty(spectrum.shape[:-1] + (frequencies.size,), dtype=np.float64)
+  for i in range(nlat):
+    f = interpolate.interp1d(frequency[:, i], spectrum[..., i, :], axis=-1,
+                             kind='linear', bounds_error=False,
+                             fill_value=np.nan, assume_sorted=True)
+    out[..., i, :] = f(frequencies)
+  return out, frequencies
+
+
+def ensemble_mean(x, axis, skipna=False):
+  """scripts/compute_ensemble_mean.py:131 -- xbeam.Mean(realization, skipna):
+  xarray / NumPy mean of float32 data (float32 result)."""
+  x = np.asarray(x)
+  with np.errstate(invalid='ignore'):
+    import warnings  # pylint: disable=import-outside-toplevel
+    with warnings.catch_warnings():
+      warnings.simplefilter('ignore', RuntimeWarning)
+      return np.nanmean(x, axis=axis) if skipna else np.mean(x, axis=axis)
+
+
 # ---------------------------------------------------------------------------
 # Map-output ("Spatial*") metrics: no spatial averaging (metrics.py:304-374,
 # 718-772, 1244-1266, 1366-1399); Metric.compute then averages over time

@@ -645,3 +645,34 @@ def test_seeps_known_answers():
                              atol=1e-4)
   np.testing.assert_allclose(orc.seeps_pointwise(t + 0.5, t, wet, wet, p1),
                              1.25, atol=1e-4)
+
+
+# ---- interpolate_spectral_frequencies (derived_variables_test.py:432-528) -----
+def _multispectral(nlat_half=30, nlon=360, seed=0):
+  rs = np.random.RandomState(seed)
+  lat = np.arange(-nlat_half, nlat_half + 1, 5.0)
+  lon = np.linspace(0, 360, nlon, endpoint=False)
+  x = rs.standard_normal((2, lat.size, nlon))
+  for k in (3, 7, 20):
+    x += np.cos(2 * np.pi * k * lon / 360)[None, None, :] * (1 + k)
+  return x.astype(np.float32), lat, lon
+
+
+def test_interpolate_spectral_frequencies_reference_properties():
+  """The two properties the reference's tests pin: with the default
+  frequencies the latitude = 0 row (the narrowest range) is unchanged
+  (derived_variables_test.py:454-462); with the frequencies of latitude 5 the
+  latitude-5 row is unchanged (:503-511).  (The "nearby rows barely change"
+  checks of the reference hold for its smooth test spectrum only.)"""
+  x, lat, lon = _multispectral()
+  dims = ('time', 'latitude', 'longitude')
+  spec, sd, freq, _ = orc.zonal_energy_spectrum(x, dims, lat, lon)
+  assert sd == ('time', 'latitude', 'zonal_wavenumber')
+  out, fr = orc.interpolate_spectral_frequencies(spec, freq)
+  i0 = int(np.where(lat == 0)[0][0])
+  np.testing.assert_allclose(fr, freq[:, i0])
+  np.testing.assert_allclose(out[:, i0], spec[:, i0], rtol=1e-9)
+  i5 = int(np.where(lat == 5)[0][0])
+  out, fr = orc.interpolate_spectral_frequencies(spec, freq, freq[3:8, i5])
+  np.testing.assert_allclose(out[:, i5], spec[:, i5, 3:8], rtol=1e-9)
+  assert out.shape == (2, lat.size, 5)

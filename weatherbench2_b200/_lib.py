@@ -121,6 +121,11 @@ PROTOTYPES = {
                                           C.c_int64, C.POINTER(Csr),
                                           C.POINTER(Csr)]),
     'wb2_wind_speed': (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    'wb2_ens_mean': (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, _I64P,
+                               C.c_int64, C.c_int, _P]),
+    'wb2_spectrum_interp': (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_double), C.c_int32,
+                                      C.POINTER(C.c_double), _P]),
     'wb2_rank_histogram': (C.c_int, [
         _P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _I64P, _I64P,
         C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64,
@@ -552,6 +557,24 @@ class Context:
   # -- derived variables -------------------------------------------------------
   def wind_speed(self, u: int, v: int, out: int, n: int):
     check(self.lib.wb2_wind_speed(self.handle, _P(u), _P(v), _P(out), int(n)))
+
+  def ens_mean(self, x: int, nmember: int, member_stride: int,
+               off_x: np.ndarray, slab: int, skipna: bool, out: int):
+    off_x = np.ascontiguousarray(off_x, dtype=np.int64)
+    check(self.lib.wb2_ens_mean(
+        self.handle, _P(x), int(nmember), int(member_stride), int(off_x.size),
+        _as_ptr(off_x, C.c_int64), int(slab), int(bool(skipna)), _P(out)))
+
+  def spectrum_interp(self, spec: int, nfield: int, nrow: int, nk: int,
+                      freq_table: np.ndarray, freqs: np.ndarray, out: int):
+    """freq_table: [nrow][nk] increasing frequencies of every latitude row."""
+    step = np.ascontiguousarray(freq_table, dtype=np.float64)
+    assert step.shape == (nrow, nk)
+    fr = np.ascontiguousarray(freqs, dtype=np.float64)
+    check(self.lib.wb2_spectrum_interp(
+        self.handle, _P(spec), int(nfield), int(nrow), int(nk),
+        _as_ptr(step, C.c_double), int(fr.size), _as_ptr(fr, C.c_double),
+        _P(out)))
 
   # -- K10 --------------------------------------------------------------------
   def rank_histogram(self, x: int, t: int, nmember: int, member_stride: int,

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdint>
@@ -118,6 +119,15 @@ class Packer {
   size_t size_ = 0;
   Slot* slot_ = nullptr;
 };
+
+// NVTX range around every compute entry point of the C ABI (visible in Nsight
+// Systems / ncu --nvtx; a no-op when no tool is attached): the trace hook
+// SURVEY.md section 5 lists.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define WB2_NVTX(name) ::wb2::NvtxRange wb2_nvtx_range_(name)
 
 struct DeviceGuard {
   int prev = -1;

@@ -27,6 +27,7 @@ using namespace wb2;
 
 extern "C" int wb2_wind_speed(wb2_ctx* ctx, const float* u, const float* v, float* out,
                               int64_t n) {
+  WB2_NVTX("wb2_wind_speed");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return WB2_OK;

@@ -483,6 +483,7 @@ extern "C" {
 int wb2_det_metrics(wb2_ctx* ctx, const void* f, const void* t, const void* c, int dtype,
                     int64_t nfield, const int64_t* off_f, const int64_t* off_t,
                     const int64_t* off_c, const wb2_weights* w, int skipna, double* out) {
+  WB2_NVTX("wb2_det_metrics");
   return det_metrics_impl(ctx, c ? MODE_CLIM : MODE_PLAIN, f, t, c, nullptr, dtype, nfield,
                           off_f, off_t, c ? off_c : nullptr, nullptr, w, skipna, out);
 }
@@ -492,6 +493,7 @@ int wb2_det_metrics_vector(wb2_ctx* ctx, const void* fu, const void* fv, const v
                            const int64_t* off_fv, const int64_t* off_tu,
                            const int64_t* off_tv, const wb2_weights* w, int skipna,
                            double* out) {
+  WB2_NVTX("wb2_det_metrics_vector");
   // operand order inside the kernel: f = fu, t = tu, c = fv, g = tv
   return det_metrics_impl(ctx, MODE_VECTOR, fu, tu, fv, tv, dtype, nfield, off_fu, off_tu,
                           off_fv, off_tv, w, skipna, out);

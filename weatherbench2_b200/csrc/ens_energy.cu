@@ -188,6 +188,7 @@ extern "C" int wb2_energy_score(wb2_ctx* ctx, const void* x, const void* t, int 
                                 int32_t nmember, int64_t member_stride, int64_t nfield,
                                 const int64_t* off_x, const int64_t* off_t,
                                 const wb2_weights* w, double* out) {
+  WB2_NVTX("wb2_energy_score");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_energy_score: only WB2_F32 inputs are supported");
   WB2_REQUIRE(nmember >= 1 && nmember <= 64,

@@ -103,6 +103,7 @@ extern "C" int wb2_ens_maps(wb2_ctx* ctx, const void* x, const void* t, int dtyp
                             const int64_t* off_x, const int64_t* off_t, int32_t nrow,
                             int32_t ncol, int64_t row_stride, int32_t stat_mask, int skipna,
                             float* out) {
+  WB2_NVTX("wb2_ens_maps");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_maps: only WB2_F32 inputs are supported");
   if (nmember < 1 || nmember > 64) {

@@ -363,6 +363,7 @@ extern "C" int wb2_ens_metrics(wb2_ctx* ctx, const void* x, const void* t, int d
                                int32_t nmember, int64_t member_stride, int64_t nfield,
                                const int64_t* off_x, const int64_t* off_t,
                                const wb2_weights* w, int skipna, double* out) {
+  WB2_NVTX("wb2_ens_metrics");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_metrics: only WB2_F32 inputs are supported");
   WB2_REQUIRE(nmember >= 1, "wb2_ens_metrics: nmember must be >= 1");

@@ -196,6 +196,7 @@ int wb2_det_metrics_host(wb2_ctx* ctx, const void* f, const void* t, const void*
                          int64_t nfield, const int64_t* off_f, const int64_t* off_t,
                          const int64_t* off_c, const wb2_weights* w, int skipna,
                          double* out_host) {
+  WB2_NVTX("wb2_det_metrics_host");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32 || dtype == WB2_F64, "dtype must be WB2_F32 or WB2_F64");
   WB2_TRY(validate_weights(w));
@@ -315,6 +316,7 @@ int wb2_ens_metrics_host(wb2_ctx* ctx, const void* x, const void* t, int dtype,
                          int32_t nmember, int64_t member_stride, int64_t nfield,
                          const int64_t* off_x, const int64_t* off_t, const wb2_weights* w,
                          int skipna, double* out_host) {
+  WB2_NVTX("wb2_ens_metrics_host");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_metrics_host: only WB2_F32 inputs are supported");
   WB2_REQUIRE(nmember >= 1, "wb2_ens_metrics_host: nmember must be >= 1");
@@ -413,6 +415,7 @@ int wb2_ens_metrics_host(wb2_ctx* ctx, const void* x, const void* t, int dtype,
 int wb2_regrid_conservative_host(wb2_ctx* ctx, const float* src, float* dst, int64_t nfield,
                                  int64_t src_field_stride, int64_t dst_field_stride,
                                  const wb2_csr* lon_w, const wb2_csr* lat_w) {
+  WB2_NVTX("wb2_regrid_conservative_host");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(lon_w && lat_w, "weights are NULL");
   WB2_REQUIRE(nfield >= 0, "nfield < 0");
@@ -563,12 +566,14 @@ static int spectrum_host(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t n
 int wb2_zonal_spectrum_host(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
                             int32_t ncol, const double* scale, float* out_host,
                             int32_t accumulate, int64_t nfield_out) {
+  WB2_NVTX("wb2_zonal_spectrum_host");
   return spectrum_host(ctx, x, nfield, nrow, ncol, scale, out_host, accumulate, nfield_out, 0);
 }
 
 int wb2_zonal_spectrum_latsum_host(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
                                    int32_t ncol, const double* scale, float* out_host,
                                    int64_t nfield_out) {
+  WB2_NVTX("wb2_zonal_spectrum_latsum_host");
   return spectrum_host(ctx, x, nfield, nrow, ncol, scale, out_host, 1, nfield_out, 1);
 }
 

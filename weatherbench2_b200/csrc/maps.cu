@@ -126,6 +126,7 @@ extern "C" int wb2_det_maps(wb2_ctx* ctx, const void* f, const void* t, int dtyp
                             int64_t nout, int32_t ngroup, const int64_t* off_f,
                             const int64_t* off_t, int32_t nrow, int32_t ncol, int64_t row_stride,
                             int skipna, void* out) {
+  WB2_NVTX("wb2_det_maps");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32 || dtype == WB2_F64, "dtype must be WB2_F32 or WB2_F64");
   WB2_REQUIRE(stat == WB2_MAP_BIAS || stat == WB2_MAP_MSE || stat == WB2_MAP_MAE,

@@ -88,6 +88,7 @@ extern "C" int wb2_rank_histogram(wb2_ctx* ctx, const float* x, const float* t,
                                   int32_t ngroup, const int64_t* off_x, const int64_t* off_t,
                                   int32_t nrow, int32_t ncol, int64_t row_stride, int32_t nbins,
                                   int32_t random_ties, uint64_t seed, float* out) {
+  WB2_NVTX("wb2_rank_histogram");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nmember >= 1 && nmember <= 65536, "nmember out of range");
   WB2_REQUIRE(nbins >= 1 && (nmember + 1) % nbins == 0,

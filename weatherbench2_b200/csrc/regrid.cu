@@ -198,6 +198,7 @@ extern "C" int wb2_regrid_conservative(wb2_ctx* ctx, const float* src, float* ds
                                        int64_t nfield, int64_t src_field_stride,
                                        int64_t dst_field_stride, const wb2_csr* lon_w,
                                        const wb2_csr* lat_w) {
+  WB2_NVTX("wb2_regrid_conservative");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_TRY(check_csr(lon_w, "longitude"));
   WB2_TRY(check_csr(lat_w, "latitude"));

@@ -78,6 +78,7 @@ using namespace wb2;
 extern "C" int wb2_regrid_gather(wb2_ctx* ctx, const float* src, float* dst, int64_t nfield,
                                  int64_t src_field_stride, int64_t dst_field_stride,
                                  int32_t nsource, int32_t ntarget, const int32_t* indices) {
+  WB2_NVTX("wb2_regrid_gather");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nfield >= 0 && nfield < 65536LL * 65536LL, "nfield out of range");
   WB2_REQUIRE(nsource > 0 && ntarget > 0, "empty grid");
@@ -109,6 +110,7 @@ extern "C" int wb2_regrid_bilinear(wb2_ctx* ctx, const float* src, float* dst, i
                                    const int32_t* lon_i0, const int32_t* lon_i1,
                                    const float* lon_t, const int32_t* lat_i0,
                                    const int32_t* lat_i1, const float* lat_t) {
+  WB2_NVTX("wb2_regrid_bilinear");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nfield >= 0 && nfield < 65536LL * 65536LL, "nfield out of range");
   WB2_REQUIRE(nlon_s > 0 && nlat_s > 0 && nlon_t > 0 && nlat_t > 0, "empty grid");

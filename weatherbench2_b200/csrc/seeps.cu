@@ -111,6 +111,7 @@ extern "C" int wb2_seeps_maps(wb2_ctx* ctx, const float* f, const float* t, cons
                               int32_t ncol, int64_t row_stride, int64_t wet_row_stride,
                               float dry_threshold, float min_p1, float max_p1, int skipna,
                               float* out) {
+  WB2_NVTX("wb2_seeps_maps");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nrow > 0 && ncol > 0 && row_stride >= ncol && wet_row_stride >= ncol,
               "bad grid: nrow=%d ncol=%d", nrow, ncol);

@@ -538,12 +538,14 @@ using namespace wb2;
 extern "C" int wb2_zonal_spectrum_latsum(wb2_ctx* ctx, const float* x, int64_t nfield,
                                          int32_t nrow, int32_t ncol, const double* scale,
                                          float* out, int64_t nfield_out) {
+  WB2_NVTX("wb2_zonal_spectrum_latsum");
   return spectrum_latsum_impl(ctx, x, nfield, nrow, ncol, scale, out, nfield_out, 0);
 }
 
 extern "C" int wb2_zonal_spectrum(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
                                   int32_t ncol, const double* scale, float* out,
                                   int32_t accumulate, int64_t nfield_out) {
+  WB2_NVTX("wb2_zonal_spectrum");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(nrow > 0 && ncol > 1, "bad grid %d x %d", nrow, ncol);
   WB2_REQUIRE(nfield >= 0, "nfield < 0");

@@ -438,6 +438,7 @@ extern "C" int wb2_ens_threshold_metrics(wb2_ctx* ctx, const void* x, const void
                                          const int64_t* off_a, const void* thr_b,
                                          const int64_t* off_b, const double* z,
                                          const wb2_weights* w, int skipna, double* out) {
+  WB2_NVTX("wb2_ens_threshold_metrics");
   WB2_TRY(check_threshold_args(ctx, dtype, nthreshold, thr_a, thr_b, off_a, off_b, z, w, out,
                                nfield));
   WB2_REQUIRE(nthreshold >= 1, "wb2_ens_threshold_metrics: nthreshold must be >= 1");
@@ -458,6 +459,7 @@ extern "C" int wb2_gaussian_metrics(wb2_ctx* ctx, const void* mean, const void* 
                                     const int64_t* off_a, const void* thr_b,
                                     const int64_t* off_b, const double* z, const wb2_weights* w,
                                     int skipna, double* out) {
+  WB2_NVTX("wb2_gaussian_metrics");
   WB2_TRY(check_threshold_args(ctx, dtype, nthreshold, thr_a, thr_b, off_a, off_b, z, w, out,
                                nfield));
   if (nfield == 0) return WB2_OK;
@@ -547,6 +549,7 @@ extern "C" int wb2_ens_threshold_maps(wb2_ctx* ctx, const void* x, const void* t
                                       const void* thr_b, const int64_t* off_b, const double* z,
                                       int32_t nrow, int32_t ncol, int64_t row_stride, int32_t stat,
                                       int skipna, float* out) {
+  WB2_NVTX("wb2_ens_threshold_maps");
   WB2_REQUIRE(ctx != nullptr, "ctx is NULL");
   WB2_REQUIRE(dtype == WB2_F32, "wb2_ens_threshold_maps: only WB2_F32 inputs are supported");
   WB2_REQUIRE(nthreshold >= 1 && nthreshold <= 4096, "nthreshold out of range");
