@@ -148,3 +148,12 @@ def test_by_valid_chunks_align_truth_by_label_not_position():
                     'latitude': lat, 'longitude': lon})
   with pytest.raises(KeyError):
     wd.evaluate_sharded(bad, truth, None, chunk_dim='time', loop_fn=loop)
+
+
+def test_prefetching_feeder_gives_the_same_result():
+  forecast, truth = _make_data(ninit=7)
+  a = wd.evaluate_sharded(forecast, truth, None, loop_fn=_oracle_loop,
+                          chunk_size=2)
+  b = wd.evaluate_sharded(forecast, truth, None, loop_fn=_oracle_loop,
+                          chunk_size=2, prefetch=2, num_threads=3)
+  np.testing.assert_array_equal(a['z'].values, b['z'].values)

@@ -116,3 +116,14 @@ def test_evaluate_sharded_on_nccl(tmp_path, world, skipna):
 def xl_lookup(coord, labels):
   from weatherbench2_b200 import xarray_lite as xl
   return xl._lookup(coord, labels.ravel()).reshape(labels.shape)  # pylint: disable=protected-access
+
+
+def test_evaluate_sharded_with_the_pinned_chunk_feeder():
+  """prefetch=2: forecast chunks are read ahead into pinned buffers
+  (feeder.ChunkFeeder) and streamed by the *_host entries; same numbers."""
+  from weatherbench2_b200 import distributed as wd
+  forecast, truth, clim = _data(ninit=5)
+  cfg = _eval_config(clim)
+  a = wd.evaluate_sharded(forecast, truth, cfg, skipna=True)
+  b = wd.evaluate_sharded(forecast, truth, cfg, skipna=True, prefetch=2)
+  np.testing.assert_array_equal(a['z'].values, b['z'].values)

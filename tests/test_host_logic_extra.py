@@ -131,3 +131,48 @@ def test_time_mean_accumulator_with_map_and_quantile_outputs():
       want = np.nanmean(full, axis=1) if skipna else full.mean(axis=1)
     np.testing.assert_allclose(got.values, want, rtol=1e-12, equal_nan=True)
     assert np.isnan(got.values[:, 0, 0, 0]).all()
+
+
+def test_upload_gathered_packs_only_referenced_slabs_and_keeps_members_plain():
+  """_spatial._upload_gathered with a fake context: a (member, time) operand
+  whose time axis is a label gather of a long record is packed to
+  members x DISTINCT times slabs; the member axis stays evenly strided (what
+  split_member_dim needs); every addressed slab holds the right data."""
+  from weatherbench2_b200 import _spatial as sp, xarray_lite as xl
+
+  class FakeCtx:
+    def __init__(self):
+      self.blobs = {}
+    def to_device(self, a):
+      a = np.ascontiguousarray(a)
+      self.blobs[a.ctypes.data] = a  # "device" memory = this host copy
+      return a.ctypes.data
+
+  rs = np.random.RandomState(0)
+  nm, nt, nlat, nlon = 3, 50, 5, 8
+  x = rs.standard_normal((nm, nt, nlat, nlon)).astype(np.float32)
+  da = xl.DataArray(x, ('realization', 'time', 'latitude', 'longitude'),
+                    {'realization': np.arange(nm), 'time': np.arange(nt),
+                     'latitude': np.linspace(-90, 90, nlat),
+                     'longitude': np.arange(nlon) * 45.0})
+  pos = np.array([[7, 9, 11], [9, 11, 13]])  # (init, lead) -> time, overlapping
+  op = sp.gather_operand(sp.prepare_operand(da),
+                         {'time': (('init', 'lead'), pos)})
+  ctx, staged = FakeCtx(), []
+  dev = sp._upload_gathered(ctx, op, staged)  # pylint: disable=protected-access
+  blob = ctx.blobs[dev.addr]
+  assert blob.shape[:2] == (nm, 4)  # 4 distinct times: 7, 9, 11, 13
+  dims, shape = dev.outer_dims, dev.outer_shape
+  table = sp.offset_table(dev, dims, shape).reshape(shape)
+  flat = blob.reshape(-1)
+  for m in range(nm):
+    for i in range(2):
+      for l in range(3):
+        idx = {'realization': m, 'init': i, 'lead': l}
+        off = table[tuple(idx[d] for d in dims)]
+        np.testing.assert_array_equal(
+            flat[off:off + nlat * nlon].reshape(nlat, nlon), x[m, pos[i, l]])
+  rest, m_, stride = sp.split_member_dim(dev, 'realization')
+  assert m_ == nm and stride == table[tuple(
+      1 if d == 'realization' else 0 for d in dims)]
+  assert 'realization' not in rest.outer_dims

@@ -418,24 +418,55 @@ def _upload_gathered(ctx: _lib.Context, op: Operand, staged: list) -> Operand:
   gather or a day-of-year climatology lookup addresses a few slabs of a long
   record: uploading the whole backing array, per variable and chunk, is what
   the round-1 review flagged), packed contiguously, and re-addresses the
-  operand through one explicit offset term."""
-  dims, shape = op.outer_dims, op.outer_shape
-  table = offset_table(op, dims, shape)
-  uniq, inv = np.unique(table, return_inverse=True)
+  operand.  Dimensions that were plain strided terms (e.g. the ensemble
+  members) stay plain strided terms of the packed copy, so that
+  split_member_dim still sees an evenly strided member axis; the looked-up
+  dimensions become one explicit offset term over the DISTINCT slabs."""
+  terms = op.gather_terms
+  plain, looked = [], []
+  for tdims, arr in terms:
+    arr = np.asarray(arr, dtype=np.int64)
+    if len(tdims) == 1 and (arr.size < 2 or
+                            (np.diff(arr) == arr[1] - arr[0]).all()):
+      plain.append((tdims[0], arr))
+    else:
+      looked.append((tuple(tdims), arr))
+  size = dict(zip(op.outer_dims, op.outer_shape))
+  gdims = tuple(d for d in op.outer_dims if any(d in td for td, _ in looked))
+  gshape = tuple(size[d] for d in gdims)
+  goff = np.zeros(gshape, dtype=np.int64)
+  for tdims, arr in looked:
+    perm = [tdims.index(d) for d in gdims if d in tdims]
+    a = np.transpose(arr, perm)
+    a = a[tuple(slice(None) if d in tdims else None for d in gdims)]
+    goff = goff + a
+  uniq, inv = np.unique(goff.reshape(-1), return_inverse=True)
   slab = (op.nrow - 1) * op.row_stride + op.ncol
   pad = (slab + 63) // 64 * 64
   es = op.itemsize
-  packed = np.empty((uniq.size, pad), dtype=op.dtype)
-  for i, off in enumerate(uniq):
-    src = np.ctypeslib.as_array(
-        (np.ctypeslib.ctypes.c_char * (slab * es)).from_address(
-            op.addr + int(off) * es)).view(op.dtype)
-    packed[i, :slab] = src
+  pshape = tuple(arr.size for _, arr in plain)
+  nplain = int(np.prod(pshape)) if pshape else 1
+  packed = np.empty((nplain, uniq.size, pad), dtype=op.dtype)
+  grids = np.meshgrid(*[arr for _, arr in plain], indexing='ij') if plain else []
+  poff = sum(grids).reshape(-1) if plain else np.zeros(1, np.int64)
+  for pi in range(nplain):
+    for ui, off in enumerate(uniq):
+      src = np.ctypeslib.as_array(
+          (np.ctypeslib.ctypes.c_char * (slab * es)).from_address(
+              op.addr + (int(poff[pi]) + int(off)) * es)).view(op.dtype)
+      packed[pi, ui, :slab] = src
   dptr = ctx.to_device(packed)
   staged.append(dptr)
   out = dataclasses.replace(op, addr=dptr, on_device=True)
-  out.gather_terms = [(tuple(dims),
-                       (inv.astype(np.int64) * pad).reshape(shape))]
+  new_terms = []
+  stride = uniq.size * pad
+  for i in range(len(plain) - 1, -1, -1):
+    d, arr = plain[i]
+    new_terms.insert(0, ((d,), np.arange(arr.size, dtype=np.int64) * stride))
+    stride *= arr.size
+  if gdims:
+    new_terms.append((gdims, (inv.astype(np.int64) * pad).reshape(gshape)))
+  out.gather_terms = new_terms
   return out
 
 
@@ -717,13 +748,14 @@ def _threshold_tables(spec, dims, shape, base, staged, ctx):
     def stage(op):
       if op.on_device:
         return op
+      if getattr(op, 'gather_terms', None) is not None:
+        # a gathered threshold field (day-of-year / quantile lookup): only the
+        # slabs it references are uploaded, re-addressed by the returned operand
+        return _to_device_operand(ctx, op, staged)
       key = id(op.data)
       if key not in seen:
         seen[key] = _to_device_operand(ctx, op, staged).addr
-      out = dataclasses.replace(op, addr=seen[key], on_device=True)
-      if hasattr(op, 'gather_terms'):
-        out.gather_terms = op.gather_terms
-      return out
+      return dataclasses.replace(op, addr=seen[key], on_device=True)
 
     ops = [stage(op) for op in spec[1]]
     return len(ops), ops, lambda b: (

@@ -123,8 +123,8 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
                      skipna: bool = False, chunk_dim: str = 'init_time',
                      chunk_size: int = 1, group=None, device=None,
                      loop_fn: t.Optional[t.Callable] = None,
-                     select_truth: t.Optional[t.Callable] = None
-                     ) -> xl.Dataset:
+                     select_truth: t.Optional[t.Callable] = None,
+                     prefetch: int = 0, num_threads: int = 2) -> xl.Dataset:
   """Time-mean metric results with the chunks of `chunk_dim` sharded over the
   process group.  Every rank returns the full (identical) result.
 
@@ -134,6 +134,11 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   loop_fn / select_truth are injectable for tests; they default to
   evaluation._metric_and_region_loop and
   evaluation.select_truth_at_valid_time.
+  prefetch > 0: this rank's forecast chunks come from a feeder.ChunkFeeder that
+  reads `prefetch` chunks ahead into pinned host buffers with `num_threads`
+  reader threads (the DatasetToChunks replacement, evaluation.py:693-705), so
+  the read of chunk i+1 overlaps the kernels of chunk i and the H2D copies run
+  at the PCIe rate.
   """
   from weatherbench2_b200 import evaluation  # pylint: disable=import-outside-toplevel
   dist = _dist()
@@ -156,10 +161,17 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   nchunks = (n + chunk_size - 1) // chunk_size
   acc = TimeMeanAccumulator(chunk_dim, skipna)
   import contextlib  # pylint: disable=import-outside-toplevel
+  mine = [int(ci) for ci in shard_indices(nchunks, rank, world)]
+  if prefetch > 0:
+    from weatherbench2_b200 import feeder  # pylint: disable=import-outside-toplevel
+    chunks = (c for _, c in feeder.ChunkFeeder(
+        forecast, chunk_dim, chunk_size, indices=mine, depth=prefetch,
+        num_threads=num_threads, pin=cache_scope is not None))
+  else:
+    chunks = (forecast.isel({chunk_dim: slice(
+        ci * chunk_size, min(n, (ci + 1) * chunk_size))}) for ci in mine)
   with (cache_scope if cache_scope is not None else contextlib.nullcontext()):
-    for ci in shard_indices(nchunks, rank, world):
-      sl = slice(int(ci) * chunk_size, min(n, (int(ci) + 1) * chunk_size))
-      fc = forecast.isel({chunk_dim: sl})
+    for fc in chunks:
       tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
       acc.add(loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True))
   if not acc.sums:
