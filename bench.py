@@ -476,7 +476,8 @@ class Harness:
       step(i)
     tail(warm=True)
     self.barrier()
-    self.sampler.start()
+    if self.rank == 0:  # one NVML poller per box (8 of them contend in the driver)
+      self.sampler.start()
     launches0 = self.ctx.launch_count
     ev0 = torch.cuda.Event(enable_timing=True)
     evk = torch.cuda.Event(enable_timing=True)
@@ -489,24 +490,32 @@ class Harness:
     tail(warm=False)
     ev1.record()
     self.barrier()
-    clocks = self.sampler.stop()
+    clocks = self.sampler.stop() if self.rank == 0 else None
     launches = self.ctx.launch_count - launches0
-    ms_total, ms_kernels = self.max_over_ranks(
-        [ev0.elapsed_time(ev1), ev0.elapsed_time(evk)])
+    mine = [ev0.elapsed_time(ev1), ev0.elapsed_time(evk)]
+    ms_total, ms_kernels = self.max_over_ranks(mine)
+    if clocks is not None and self.world > 1:
+      # spread of the per-rank kernel times (the job time is the max)
+      lo = self.max_over_ranks([-mine[1]])[0]
+      clocks['kernel_ms_per_step_min_max_over_ranks'] = [
+          -lo / max(steps, 1), ms_kernels / max(steps, 1)]
+    elif self.world > 1:
+      self.max_over_ranks([-mine[1]])
     return ms_total, ms_kernels, int(launches), clocks
 
   def time_host(self, fn, steps):
     """End-to-end region: host clock around `steps` synchronous operator calls
     (each returns with the result in host memory), max over ranks."""
     self.barrier()
-    self.sampler.start()
+    if self.rank == 0:
+      self.sampler.start()
     t0 = time.perf_counter()
     out = None
     for i in range(steps):
       out = fn(i)
     self.torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    clocks = self.sampler.stop()
+    clocks = self.sampler.stop() if self.rank == 0 else None
     (dt,) = self.max_over_ranks([dt])
     return dt, out, clocks
 
@@ -713,7 +722,8 @@ def bench_crps(h):
       'member_cells_per_s': h.world * points * ENS_M * args.steps / (ms_total * 1e-3),
       'ms_per_step': ms_total / args.steps, 'scaling': 'weak',
       'gpu_launches': launches, 'clocks': clocks,
-      'roofline': h.roofline('crps_sweep', 'ens_metrics_kernel<50,...> + finalize',
+      'roofline': h.roofline('crps_sweep', 'ens_pair_kernel<50> (two points per lane, packed '
+                             'f32x2 sorting network) + finalize',
                              points * ENS_BYTES_PER_POINT,
                              ms_kernels / args.steps),
   }

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu"
 $NCU -k regex:det_tma_kernel -s 3 -c 1 -f -o gpurun_out/r2_ncu_rmse_acc $B --workloads none > gpurun_out/ncu_rmse_acc.log 2>&1
-$NCU -k regex:ens_metrics_kernel -s 3 -c 1 -f -o gpurun_out/r2_ncu_crps_sweep $B --workloads crps > gpurun_out/ncu_crps.log 2>&1
+$NCU -k "regex:ens_pair_kernel|ens_metrics_kernel" -s 3 -c 1 -f -o gpurun_out/r2_ncu_crps_sweep $B --workloads crps > gpurun_out/ncu_crps.log 2>&1
 $NCU -k regex:regrid -s 3 -c 1 -f -o gpurun_out/r2_ncu_regrid $B --workloads regrid > gpurun_out/ncu_regrid.log 2>&1
 $NCU -k regex:spectrum_pfa_kernel -s 3 -c 1 -f -o gpurun_out/r2_ncu_spectrum_sweep $B --workloads spectrum > gpurun_out/ncu_spectrum.log 2>&1
 $NCU -k regex:spectrum_pfa_kernel -s 7 -c 1 -f -o gpurun_out/r2_ncu_spectrum_latsum $B --workloads spectrum > gpurun_out/ncu_latsum.log 2>&1

@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(kEnsThreads, OCC) ens_pair_kernel(const EnsPar
   const int64_t field = blockIdx.x / p.nblk;
   const int blk = blockIdx.x % p.nblk;
   const int R = p.nregion;
-  const float fm = float(MP);
   const float* __restrict__ px = p.x + p.off_x[field];
   const float* __restrict__ pt = p.t + p.off_t[field];
   const bool zero_skip = p.zero_skip != 0;
@@ -204,7 +203,11 @@ __global__ void __launch_bounds__(kEnsThreads, OCC) ens_pair_kernel(const EnsPar
       float sx0, sx1, t0, t1;
       unpk2f(sumx, sx0, sx1);
       unpk2f(t2, t0, t1);
-      const float mean0 = sx0 / fm, mean1 = sx1 / fm;
+      // divisions by the constants M and M - 1 as multiplications by their
+      // float reciprocals (the IEEE division is a ~15-instruction subroutine,
+      // eight of them per pair; differs from it by <= 1 ulp)
+      constexpr float inv_m = 1.f / float(MP), inv_m1 = 1.f / float(MP - 1);
+      const float mean0 = sx0 * inv_m, mean1 = sx1 * inv_m;
       const u64x2f mean2 = pk2f(mean0, mean1);
       u64x2f ss = 0ull;
 #pragma unroll
@@ -224,20 +227,20 @@ __global__ void __launch_bounds__(kEnsThreads, OCC) ens_pair_kernel(const EnsPar
       unpk2f(s2, s0, s1);
       float val0[kEnsStats], val1[kEnsStats];
       {
-        const float var = ss0 / (fm - 1.f), dm = t0 - mean0, mse = dm * dm;
-        val0[0] = sa0 / fm;
-        val0[1] = sx0 == sx0 ? 2.f * (s0 / fm) / (fm - 1.f) : nanf_;
+        const float var = ss0 * inv_m1, dm = t0 - mean0, mse = dm * dm;
+        val0[0] = sa0 * inv_m;
+        val0[1] = sx0 == sx0 ? 2.f * (s0 * inv_m) * inv_m1 : nanf_;
         val0[2] = mse;
         val0[3] = var;
-        val0[4] = mse - var / fm;
+        val0[4] = mse - var * inv_m;
       }
       {
-        const float var = ss1 / (fm - 1.f), dm = t1 - mean1, mse = dm * dm;
-        val1[0] = sa1 / fm;
-        val1[1] = sx1 == sx1 ? 2.f * (s1 / fm) / (fm - 1.f) : nanf_;
+        const float var = ss1 * inv_m1, dm = t1 - mean1, mse = dm * dm;
+        val1[0] = sa1 * inv_m;
+        val1[1] = sx1 == sx1 ? 2.f * (s1 * inv_m) * inv_m1 : nanf_;
         val1[2] = mse;
         val1[3] = var;
-        val1[4] = mse - var / fm;
+        val1[4] = mse - var * inv_m;
       }
 #pragma unroll
       for (int i = 0; i < kEnsStats; ++i) acc[i] += val0[i] + val1[i];
