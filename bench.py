@@ -959,7 +959,15 @@ def main():
                         ('regrid', 'regrid', bench_regrid),
                         ('spectrum', 'spectrum_sweep', bench_spectrum)):
     if key in wanted:
-      workloads[name] = fn(h)
+      if h.world == 1:
+        try:
+          workloads[name] = fn(h)
+        except Exception as e:  # pylint: disable=broad-except
+          # a failed workload must not take the contract line with it (under
+          # torchrun an exception ends the job anyway: ranks meet in collectives)
+          workloads[name] = {'error': f'{type(e).__name__}: {e}'[:400]}
+      else:
+        workloads[name] = fn(h)
       torch.cuda.empty_cache()
   line['workloads'] = workloads
   if h.rank == 0 and not args.no_cpu:
