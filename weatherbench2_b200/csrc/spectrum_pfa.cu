@@ -269,9 +269,13 @@ constexpr int idem(int n2, int r) {  // CRT idempotent: 1 mod r, 0 mod n2 / r
   return x % n2;
 }
 
-template <int RA_, int RB_, int RC_, int G_, int NT_, int MINB_ = 2>
+// TWG_: read the split twiddles from global memory (L1) instead of a per-CTA
+// shared copy -- 11.5 KB less shared memory per CTA, which is what a fourth CTA
+// per SM needs.
+template <int RA_, int RB_, int RC_, int G_, int NT_, int MINB_ = 2, int TWG_ = 0>
 struct Plan {
   static constexpr int RA = RA_, RB = RB_, RC = RC_, G = G_, NT = NT_, MINB = MINB_;
+  static constexpr int TWG = TWG_;
   static constexpr int N2 = RA * RB * RC, NK = N2 + 1, N = 2 * N2;
   static constexpr int SA = N2 / RA, SB = N2 / RB, SC = N2 / RC;  // Good's input map
   static constexpr int EA = idem(N2, RA), EB = idem(N2, RB), EC = idem(N2, RC);
@@ -284,7 +288,7 @@ struct Plan {
   static constexpr int kRowBytes = N * 4;
   static constexpr int kStageBytes = 2 * G * kRowBytes;
   static constexpr int kWorkBytes = G * N2 * 16;
-  static constexpr int kTwnBytes = N2 * 16;
+  static constexpr int kTwnBytes = TWG ? 0 : N2 * 16;
   static constexpr int kTaskBytes = ((NTC * 16 + 127) / 128) * 128;
   static constexpr int kSmem = kStageBytes + kWorkBytes + kTwnBytes + kTaskBytes + 64;
   // thread slots per row pair, padded to half-warps so that the 64-bit shared
@@ -367,7 +371,8 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
   u64* work_re = reinterpret_cast<u64*>(smem + P::kStageBytes);
   u64* work_im = work_re + G * N2;
   const ulonglong2* twn =
-      reinterpret_cast<const ulonglong2*>(smem + P::kStageBytes + P::kWorkBytes);
+      P::TWG ? reinterpret_cast<const ulonglong2*>(p.twn)
+             : reinterpret_cast<const ulonglong2*>(smem + P::kStageBytes + P::kWorkBytes);
   const int4* ctask = reinterpret_cast<const int4*>(smem + P::kStageBytes + P::kWorkBytes +
                                                      P::kTwnBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + P::kStageBytes + P::kWorkBytes +
@@ -376,8 +381,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
   const int tid = threadIdx.x;
 
   {
-    float4* d = reinterpret_cast<float4*>(smem + P::kStageBytes + P::kWorkBytes);
-    for (int i = tid; i < N2; i += NT) d[i] = p.twn[i];
+    if (!P::TWG) {
+      float4* d = reinterpret_cast<float4*>(smem + P::kStageBytes + P::kWorkBytes);
+      for (int i = tid; i < N2; i += NT) d[i] = p.twn[i];
+    }
     int4* t = reinterpret_cast<int4*>(smem + P::kStageBytes + P::kWorkBytes + P::kTwnBytes);
     for (int i = tid; i < P::NTC; i += NT) t[i] = p.ctask[i];
   }
@@ -993,15 +1000,22 @@ int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
       if (plan && plan[0] == 'w')  // warp-specialised pipeline, one CTA per SM
         rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 3>, true>(ctx, x, nfield, nrow, scale, out,
                                                                mode, nslot);
+      else if (plan && plan[0] == '4')  // 4 CTAs per SM (102 registers, twiddles via L1)
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 4, 1>>(ctx, x, nfield, nrow, scale, out,
+                                                            mode, nslot);
       else if (plan && plan[0] == '0')
         rc = pfa::launch<pfa::Plan<9, 16, 5, 3, 256, 2>>(ctx, x, nfield, nrow, scale, out, mode,
                                                          nslot);
       else if (plan && plan[0] == '2')
         rc = pfa::launch<pfa::Plan<9, 16, 5, 1, 96, 5>>(ctx, x, nfield, nrow, scale, out, mode,
                                                         nslot);
-      else  // default: 3 CTAs of 5 warps per SM (measured best)
+      else if ((plan && plan[0] == '1') || mode == 0)
+        // per-time output: 3 CTAs of 5 warps per SM (measured best)
         rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 3>>(ctx, x, nfield, nrow, scale, out, mode,
                                                          nslot);
+      else  // time sum / latitude reduction: 4 CTAs per SM measured 4-7 % faster
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 4, 1>>(ctx, x, nfield, nrow, scale, out,
+                                                            mode, nslot);
       break;
     }
     case 720: rc = pfa::launch<pfa::Plan<9, 8, 5, 5, 256>>(ctx, x, nfield, nrow, scale, out,
