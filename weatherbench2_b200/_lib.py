@@ -291,6 +291,13 @@ class Context:
 
   def close(self):
     if not self._closed:
+      for bufs in self._pinned_pool.values():  # pooled result buffers
+        for ptr in bufs:
+          try:
+            self.lib.wb2_host_free(self.handle, _P(ptr))
+          except Exception:  # pylint: disable=broad-except
+            pass
+      self._pinned_pool.clear()
       self._closed = True
       self.lib.wb2_destroy(self.handle)
 
@@ -357,9 +364,11 @@ class Context:
         shape)
 
   def _release_pinned(self, ptr: int, cap: int):
+    if self._closed:
+      return  # the context is gone: a result that outlived it keeps its buffer
     pool = self._pinned_pool.setdefault(cap, [])
     held = sum(len(v) * k for k, v in self._pinned_pool.items())
-    if self._closed or held + cap > self._pinned_pool_limit:
+    if held + cap > self._pinned_pool_limit:
       try:
         self.host_free(ptr)
       except Exception:  # pylint: disable=broad-except
