@@ -226,3 +226,42 @@ def test_torch_inputs_still_being_produced_are_ordered():
     want, _ = orc.mse(fh, dims, th, dims, lat, lon)
     np.testing.assert_allclose(got, want, rtol=NORTH_STAR_RTOL)
     np.testing.assert_allclose(np.asarray(maps), (fh - th) ** 2, rtol=1e-6)
+
+
+@pytest.mark.parametrize('m', [10, 50])
+def test_k2_pair_kernel_with_a_large_offset_and_small_spread(m):
+  """Temperature-like members (~ 280 with a spread of 0.5): the pair kernel
+  sorts the MEAN-REMOVED members with hi = (a + b) - lo, so its rounding must
+  stay relative to the spread, not to the 280 (the reference forms the rank sum
+  in float64, weatherbench2/metrics.py:804-813)."""
+  from weatherbench2_b200 import _lib, _spatial as sp
+  ctx = _lib.default_context(0)
+  nlat, nlon = 91, 180
+  rs = np.random.RandomState(m)
+  x = (280.0 + 0.5 * rs.standard_normal((m, 2, nlat, nlon))).astype(np.float32)
+  t = (280.0 + 0.5 * rs.standard_normal((2, nlat, nlon))).astype(np.float32)
+  lat = np.linspace(-90, 90, nlat)
+  lon = np.linspace(0, 360, nlon, endpoint=False)
+  dx, dt_ = ctx.to_device(x), ctx.to_device(t)
+  base = min(dx, dt_)
+  slab = nlat * nlon
+  (_, spec), = sp.build_weights(ctx, lat, lon, [None], 'lat_lon', nlon)
+  out = ctx.malloc(2 * _lib.ENS_NSTAT * 8)
+  try:
+    off = np.arange(2, dtype=np.int64) * slab
+    ctx.ens_metrics(base, base, _lib.F32, m, 2 * slab, off + (dx - base) // 4,
+                    off + (dt_ - base) // 4, spec, False, out)
+    st = ctx.from_device(out, (2, _lib.ENS_NSTAT), np.float64)
+  finally:
+    for p in (dx, dt_, out):
+      ctx.free(p)
+  fd = ('realization', 'b', 'latitude', 'longitude')
+  kw = dict(lat=lat, lon=lon)
+  want = np.stack([
+      orc.crps_skill(x, fd, t, fd[1:], 'realization', **kw)[0],
+      orc.crps_spread(x, fd, 'realization', **kw)[0],
+      orc.ensemble_mean_mse(x, fd, t, fd[1:], 'realization', **kw)[0],
+      orc.ensemble_variance(x, fd, 'realization', **kw)[0],
+      orc.debiased_ensemble_mean_mse(x, fd, t, fd[1:], 'realization', **kw)[0]],
+      axis=-1)
+  np.testing.assert_allclose(st[:, :5] / st[:, 5:], want, rtol=NORTH_STAR_RTOL)
