@@ -171,7 +171,7 @@ def test_pfa_full_size_parseval(monkeypatch):
   _check(got[:1], _want(x[:1], scale))
 
 
-@pytest.mark.parametrize('plan', ['0', '1', '2', '4', 'w'])
+@pytest.mark.parametrize('plan', ['0', '1', '2', '4', 'd', 'w'])
 def test_alternative_cta_shapes_give_the_same_spectra(monkeypatch, plan):
   """WB2_PFA_PLAN selects the CTA shape of the 1440-longitude kernel: '0' =
   2 CTAs x 8 warps, '2' = 5 CTAs x 3 warps, 'w' = the warp-specialised pipeline

@@ -272,10 +272,13 @@ constexpr int idem(int n2, int r) {  // CRT idempotent: 1 mod r, 0 mod n2 / r
 // TWG_: read the split twiddles from global memory (L1) instead of a per-CTA
 // shared copy -- 11.5 KB less shared memory per CTA, which is what a fourth CTA
 // per SM needs.
-template <int RA_, int RB_, int RC_, int G_, int NT_, int MINB_ = 2, int TWG_ = 0>
+// DW_: two work buffers, alternating between items: stage A of item i + 1 may
+// then start while slower warps are still in stage C of item i (one CTA
+// barrier per item less, and a natural overlap of the two 5-warp stages).
+template <int RA_, int RB_, int RC_, int G_, int NT_, int MINB_ = 2, int TWG_ = 0, int DW_ = 0>
 struct Plan {
   static constexpr int RA = RA_, RB = RB_, RC = RC_, G = G_, NT = NT_, MINB = MINB_;
-  static constexpr int TWG = TWG_;
+  static constexpr int TWG = TWG_, DW = DW_;
   static constexpr int N2 = RA * RB * RC, NK = N2 + 1, N = 2 * N2;
   static constexpr int SA = N2 / RA, SB = N2 / RB, SC = N2 / RC;  // Good's input map
   static constexpr int EA = idem(N2, RA), EB = idem(N2, RB), EC = idem(N2, RC);
@@ -290,7 +293,8 @@ struct Plan {
   static constexpr int kWorkBytes = G * N2 * 16;
   static constexpr int kTwnBytes = TWG ? 0 : N2 * 16;
   static constexpr int kTaskBytes = ((NTC * 16 + 127) / 128) * 128;
-  static constexpr int kSmem = kStageBytes + kWorkBytes + kTwnBytes + kTaskBytes + 64;
+  static constexpr int kWorkAll = (DW ? 2 : 1) * kWorkBytes;
+  static constexpr int kSmem = kStageBytes + kWorkAll + kTwnBytes + kTaskBytes + 64;
   // thread slots per row pair, padded to half-warps so that the 64-bit shared
   // accesses of a half-warp stay inside one row pair (conflict-free strides)
   static constexpr int PTB = (NTB + 15) / 16 * 16, PTC = (NTC + 15) / 16 * 16;
@@ -370,22 +374,24 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
   // costs four MOVs per store)
   u64* work_re = reinterpret_cast<u64*>(smem + P::kStageBytes);
   u64* work_im = work_re + G * N2;
+  u64* const work_base = work_re;
   const ulonglong2* twn =
       P::TWG ? reinterpret_cast<const ulonglong2*>(p.twn)
-             : reinterpret_cast<const ulonglong2*>(smem + P::kStageBytes + P::kWorkBytes);
-  const int4* ctask = reinterpret_cast<const int4*>(smem + P::kStageBytes + P::kWorkBytes +
+             : reinterpret_cast<const ulonglong2*>(smem + P::kStageBytes + P::kWorkAll);
+  const int4* ctask = reinterpret_cast<const int4*>(smem + P::kStageBytes + P::kWorkAll +
                                                      P::kTwnBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + P::kStageBytes + P::kWorkBytes +
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + P::kStageBytes + P::kWorkAll +
                                                P::kTwnBytes + P::kTaskBytes);
   float* tile = reinterpret_cast<float*>(work_re);  // flush tile [2 G][NK], aliases `work`
+  uint32_t wsel = 0;  // DW: which work buffer the current item uses
   const int tid = threadIdx.x;
 
   {
     if (!P::TWG) {
-      float4* d = reinterpret_cast<float4*>(smem + P::kStageBytes + P::kWorkBytes);
+      float4* d = reinterpret_cast<float4*>(smem + P::kStageBytes + P::kWorkAll);
       for (int i = tid; i < N2; i += NT) d[i] = p.twn[i];
     }
-    int4* t = reinterpret_cast<int4*>(smem + P::kStageBytes + P::kWorkBytes + P::kTwnBytes);
+    int4* t = reinterpret_cast<int4*>(smem + P::kStageBytes + P::kWorkAll + P::kTwnBytes);
     for (int i = tid; i < P::NTC; i += NT) t[i] = p.ctask[i];
   }
   Cursor cur;
@@ -436,6 +442,12 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
   while (cur.valid(p)) {
     Cursor nxt = cur;
     nxt.advance(p);
+    if (P::DW) {
+      work_re = work_base + wsel * (P::kWorkBytes / 8);
+      work_im = work_re + G * N2;
+      tile = reinterpret_cast<float*>(work_re);
+      wsel ^= 1u;
+    }
     mbar_wait(full, parity);
     parity ^= 1u;
 
@@ -581,7 +593,10 @@ __global__ void __launch_bounds__(P::NT, P::MINB) spectrum_pfa_kernel(const Para
         }
       }
     }
-    __syncthreads();  // `work` (and the tile) may be overwritten by the next stage A
+    // one work buffer: it (and the tile in it) is overwritten by the next stage
+    // A; two: the next item writes the other one, and the one after that is
+    // behind the two barriers of the next item
+    if (!P::DW) __syncthreads();
     cur = nxt;
   }
 }
@@ -1013,6 +1028,9 @@ int spectrum_pfa_try(wb2_ctx* ctx, const float* x, int64_t nfield, int32_t nrow,
         // per-time output: 3 CTAs of 5 warps per SM (measured best)
         rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 3>>(ctx, x, nfield, nrow, scale, out, mode,
                                                          nslot);
+      else if (plan && plan[0] == 'd')  // double work buffer, 3 CTAs, twiddles via L1
+        rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 3, 1, 1>>(ctx, x, nfield, nrow, scale, out,
+                                                               mode, nslot);
       else  // time sum / latitude reduction: 4 CTAs per SM measured 4-7 % faster
         rc = pfa::launch<pfa::Plan<9, 16, 5, 2, 160, 4, 1>>(ctx, x, nfield, nrow, scale, out,
                                                             mode, nslot);
