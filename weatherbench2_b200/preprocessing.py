@@ -37,12 +37,10 @@ def compute_ensemble_mean(dataset, realization_name: str = REALIZATION,
     m = work.sizes[realization_name]
     shape = tuple(work.sizes[d] for d in dims)
     cells = int(np.prod(shape)) if shape else 1
-    # fields of <= 2^31 cells, <= 65535 per launch: split the flat cell range
-    nfield = max(1, -(-cells // (1 << 24)))
-    while cells % nfield:
-      nfield += 1
-    slab = cells // nfield
-    off = np.arange(nfield, dtype=np.int64) * slab
+    # one flat "field" per variable: the kernel walks it with a 64-bit
+    # grid-stride loop, members `cells` elements apart
+    slab = cells
+    off = np.zeros(1, dtype=np.int64)
     coords = {k: c for k, c in work.coords.items()
               if realization_name not in c.dims}
     if xl._is_torch(data) and data.is_cuda:  # pylint: disable=protected-access
