@@ -981,3 +981,81 @@ def rank_histogram_one_hot(f, fdims, t, tdims, ens_dim, num_bins=None):
     raise ValueError(f"Cannot bin data with ensemble_size={m} into {nb} bins")
   ranks = ranks // (default_bins // nb)  # :1950-1958
   return np.eye(nb)[ranks], od + ("bins",)
+
+
+# ----------------------------------------------------------------------------
+# Baseline forecasts built from climatology / observations --
+# weatherbench2/evaluation.py:165-193, 450-472, 607-656; utils.py:47-70.
+# Plain loops over time stamps (Python datetimes via pandas), one slab at a
+# time: what xarray's vectorised `.sel` materialises.
+# ----------------------------------------------------------------------------
+def _stamp_fields(times):
+  import pandas as pd  # local: only these helpers need calendar arithmetic
+  idx = pd.DatetimeIndex(np.asarray(times).ravel())
+  return (np.asarray(idx.year), np.asarray(idx.dayofyear),
+          np.asarray(idx.hour))
+
+
+def climatology_like_forecast(clim, clim_dims, dayofyear, hour, valid_times):
+  """`climatology.sel(dayofyear=vt.dt.dayofyear, hour=vt.dt.hour)`
+  (evaluation.py:452-457).  `clim_dims` must contain 'dayofyear' and may
+  contain 'hour'; returns (array, dims) with valid_times' axes first (named
+  'vt0', 'vt1', ...) followed by the remaining climatology dims."""
+  vt = np.asarray(valid_times)
+  _, doy, hr = _stamp_fields(vt)
+  has_hour = "hour" in clim_dims
+  rest = [d for d in clim_dims if d not in ("dayofyear", "hour")]
+  lead = ["dayofyear"] + (["hour"] if has_hour else [])
+  c = np.transpose(clim, [clim_dims.index(d) for d in lead + rest])
+  doy_pos = {int(d): i for i, d in enumerate(np.asarray(dayofyear))}
+  hour_pos = ({int(h): i for i, h in enumerate(np.asarray(hour))}
+              if has_hour else None)
+  out = np.empty((vt.size,) + c.shape[len(lead):], dtype=clim.dtype)
+  for n in range(vt.size):
+    slab = c[doy_pos[int(doy[n])]]
+    if has_hour:
+      slab = slab[hour_pos[int(hr[n])]]
+    out[n] = slab
+  out = out.reshape(vt.shape + out.shape[1:])
+  return out, tuple(f"vt{i}" for i in range(vt.ndim)) + tuple(rest)
+
+
+def persistence_like_forecast_by_init(obs, obs_times, init_times, n_lead):
+  """`truth.sel(time=init_time).expand_dims(lead_time=...)`
+  (evaluation.py:644-651): array (init_time, lead_time, ...)."""
+  pos = {np.datetime64(t, "ns"): i for i, t in enumerate(np.asarray(obs_times))}
+  rows = [obs[pos[np.datetime64(t, "ns")]] for t in np.asarray(init_times)]
+  at_init = np.stack(rows)
+  return np.repeat(at_init[:, None], n_lead, axis=1)
+
+
+def persistence_like_forecast_by_valid(obs, obs_times, times, leads):
+  """evaluation.py:165-193: valid times from `times[0] + max(leads)` on; the
+  observation at `valid time - lead` for every (time, lead).  Returns
+  (kept_times, array (time, lead_time, ...))."""
+  times = np.asarray(times)
+  leads = np.asarray(leads)
+  kept = times[times >= times[0] + leads.max()]
+  pos = {np.datetime64(t, "ns"): i for i, t in enumerate(np.asarray(obs_times))}
+  out = np.stack([np.stack([obs[pos[np.datetime64(t - l, "ns")]]
+                            for l in leads]) for t in kept])
+  return kept, out
+
+
+def probabilistic_climatology(truth, times, start_year, end_year,
+                              hour_interval):
+  """utils.py:47-70: years stacked as members.  `truth` has time first.
+  Returns (hours, dayofyear labels, array (hour, number, dayofyear, ...)) with
+  NaN where a year has no value for that day (e.g. day 366)."""
+  year, doy, hr = _stamp_fields(times)
+  hours = list(range(0, 24, hour_interval))
+  years = list(range(start_year, end_year + 1))
+  wanted = [(y in years) and (h in hours) for y, h in zip(year, hr)]
+  days = sorted({int(d) for d, w in zip(doy, wanted) if w})
+  out = np.full((len(hours), len(years), len(days)) + truth.shape[1:], np.nan,
+                dtype=truth.dtype)
+  for n in range(len(year)):
+    if wanted[n]:
+      out[hours.index(int(hr[n])), years.index(int(year[n])),
+          days.index(int(doy[n]))] = truth[n]
+  return np.array(hours), np.array(days), out

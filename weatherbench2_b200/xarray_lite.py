@@ -270,6 +270,11 @@ class DataArray:
         out = out._vectorized_sel(d, label, method)
         continue
       ind = out._label_indexer(d, label, method)
+      if (isinstance(label, slice) and d not in ('latitude', 'longitude') and
+          ind.size and (np.diff(ind) == 1).all()):
+        # a contiguous label range of an outer dimension stays a VIEW (same
+        # strides, shifted base) instead of a fancy-index copy of the data
+        ind = slice(int(ind[0]), int(ind[-1]) + 1)
       if isinstance(label, DataArray) and label.ndim == 1 and (
           label.dims[0] != d):
         out = out._vectorized_sel(d, label, method)
@@ -970,13 +975,30 @@ class LazyGather(DataArray):
   @property
   def _data(self):
     if self._materialised is None:
+      # xarray's vectorised indexing: indexers that share dimensions are
+      # applied POINTWISE along them (the day-of-year / hour lookup of one
+      # valid time), not as an outer product.
       v = self._source.values
       sdims = list(self._source.dims)
-      for d, (tdims, pos) in self._index_maps.items():
-        ax = sdims.index(d)
-        v = np.take(v, pos, axis=ax)
-        sdims[ax:ax + 1] = list(tdims)
-      perm = [sdims.index(d) for d in self._lazy_dims]
+      mapped = [d for d in sdims if d in self._index_maps]
+      jdims, jshape = [], []
+      for d in mapped:
+        tdims, pos = self._index_maps[d]
+        for td, tn in zip(tdims, pos.shape):
+          if td not in jdims:
+            jdims.append(td)
+            jshape.append(tn)
+      rest = [d for d in sdims if d not in self._index_maps]
+      v = np.transpose(v, [sdims.index(d) for d in mapped + rest])
+      index = []
+      for d in mapped:
+        tdims, pos = self._index_maps[d]
+        p = np.transpose(pos, [tdims.index(td) for td in jdims if td in tdims])
+        p = p[tuple(slice(None) if td in tdims else None for td in jdims)]
+        index.append(np.broadcast_to(p, jshape))
+      v = v[tuple(index)] if index else v
+      have = jdims + rest
+      perm = [have.index(d) for d in self._lazy_dims]
       self._materialised = np.transpose(v, perm)
     return self._materialised
 
