@@ -13,7 +13,8 @@ import fake_ctx
 from test_evaluation_gpu import _mock
 
 
-def test_config0_rmse_64x64_plumbing(tmp_path):
+def case_config0_rmse_64x64_plumbing(tmp_path, scope, crps_rtol=1e-5,
+                                     det_rtol=2e-6):
   from weatherbench2_b200 import config, evaluation, metrics
   forecast, truth, fv, tv, lat, lon, fdims, _ = _mock(
       levels=(500,), variables=('geopotential',))
@@ -24,10 +25,11 @@ def test_config0_rmse_64x64_plumbing(tmp_path):
                          output_dir=str(tmp_path)), by_init=True)
   eval_configs = {'deterministic': config.Eval(
       metrics={'rmse': metrics.RMSESqrtBeforeTimeAvg(), 'mse': metrics.MSE()})}
-  with fake_ctx.installed() as fake:
+  with scope() as fake:
     out = evaluation.evaluate_in_memory(data_config, eval_configs)
   # ONE pass over the chunk serves both metrics (the reference makes two)
-  assert [c[0] for c in fake.calls] == ['det_metrics']
+  if fake is not None:
+    assert [c[0] for c in fake.calls] == ['det_metrics']
   res = out['deterministic']['geopotential']
   assert res.dims == ('metric', 'lead_time', 'level')
   f, t = fv['geopotential'], tv['geopotential']
@@ -36,10 +38,10 @@ def test_config0_rmse_64x64_plumbing(tmp_path):
                  for l in range(nlead)])
   want, wd = orc.rmse_sqrt_before_time_avg(f, fdims, tg, fdims, lat, lon)
   np.testing.assert_allclose(res.values[0], want.mean(axis=wd.index('time')),
-                             rtol=2e-6)
+                             rtol=det_rtol)
   want, wd = orc.mse(f, fdims, tg, fdims, lat, lon)
   np.testing.assert_allclose(res.values[1], want.mean(axis=wd.index('time')),
-                             rtol=2e-6)
+                             rtol=det_rtol)
 
 
 # ------------------------------------------------------------------------------
@@ -222,7 +224,8 @@ def _rmse_time_mean(f, t, dims, lat, lon, avg):
   return want.mean(axis=wd.index(avg)), tuple(d for d in wd if d != avg)
 
 
-def test_evaluate_climatology_and_persistence_in_memory(tmp_path):
+def case_evaluate_climatology_and_persistence_in_memory(tmp_path, scope, crps_rtol=1e-5,
+                                                        det_rtol=2e-6):
   """evaluate_in_memory with the baseline-forecast switches of config.Eval
   (evaluation.py:450-472) against the oracle on materialised arrays."""
   from weatherbench2_b200 import config, evaluation, metrics
@@ -238,7 +241,7 @@ def test_evaluate_climatology_and_persistence_in_memory(tmp_path):
   tg = np.stack([np.stack([tarr['geopotential'][tpos[v]] for v in row])
                  for row in vt])
   dims = ('time', 'lead_time', 'level', 'longitude', 'latitude')
-  with fake_ctx.installed():
+  with scope():
     out = evaluation.evaluate_in_memory(dc, {
         'clim': config.Eval(metrics=mets, evaluate_climatology=True),
         'pers': config.Eval(metrics=mets, evaluate_persistence=True)})
@@ -248,24 +251,25 @@ def test_evaluate_climatology_and_persistence_in_memory(tmp_path):
   want, wd = _rmse_time_mean(cf, tg, dims, lat, lon, 'time')
   res = out['clim']['geopotential']
   assert res.dims == ('metric',) + wd
-  np.testing.assert_allclose(res.values[0], want, rtol=2e-6)
+  np.testing.assert_allclose(res.values[0], want, rtol=det_rtol)
   pf = orc.persistence_like_forecast_by_init(tarr['geopotential'], ttimes,
                                              itimes, lead.size)
   want, wd = _rmse_time_mean(pf, tg, dims, lat, lon, 'time')
   res = out['pers']['geopotential']
   assert res.dims == ('metric',) + wd
-  np.testing.assert_allclose(res.values[0], want, rtol=2e-6)
+  np.testing.assert_allclose(res.values[0], want, rtol=det_rtol)
   assert res.values[0][0].max() == 0  # lead 0: persistence IS the truth
 
 
-def test_evaluate_persistence_by_valid_in_memory(tmp_path):
+def case_evaluate_persistence_by_valid_in_memory(tmp_path, scope, crps_rtol=1e-5,
+                                                 det_rtol=2e-6):
   from weatherbench2_b200 import config, evaluation, metrics
   lat, lon = _grid()
   truth, tarr, ttimes, _ = _truth('2020-01-01', '2020-01-12', 6)
   fc, _, vtimes, lead = _forecast('2020-01-02', '2020-01-08', 12, [0, 12, 24],
                                   False)
   dc = _data_config(fc, truth, tmp_path, False)
-  with fake_ctx.installed():
+  with scope():
     out = evaluation.evaluate_in_memory(dc, {'pers': config.Eval(
         metrics={'rmse': metrics.RMSESqrtBeforeTimeAvg()},
         evaluate_persistence=True)})
@@ -278,10 +282,11 @@ def test_evaluate_persistence_by_valid_in_memory(tmp_path):
   want, wd = _rmse_time_mean(pf, tk, dims, lat, lon, 'time')
   res = out['pers']['geopotential']
   assert res.dims == ('metric',) + wd
-  np.testing.assert_allclose(res.values[0], want, rtol=2e-6)
+  np.testing.assert_allclose(res.values[0], want, rtol=det_rtol)
 
 
-def test_evaluate_probabilistic_climatology_crps_in_memory(tmp_path):
+def case_evaluate_probabilistic_climatology_crps_in_memory(tmp_path, scope, crps_rtol=1e-5,
+                                                           det_rtol=2e-6):
   from weatherbench2_b200 import config, evaluation, metrics
   lat, lon = _grid(5, 6)
   truth, tarr, ttimes, _ = _truth('2018-01-01', '2021-01-10', 12, levels=(500,),
@@ -290,14 +295,15 @@ def test_evaluate_probabilistic_climatology_crps_in_memory(tmp_path):
   fc, _, itimes, lead = _forecast('2020-02-27', '2020-03-02', 24, [0, 12], True,
                                   levels=(500,), nlat=5, nlon=6)
   dc = _data_config(fc, truth, tmp_path, True)
-  with fake_ctx.installed() as fake:
+  with scope() as fake:
     out = evaluation.evaluate_in_memory(dc, {'pc': config.Eval(
         metrics={'crps': metrics.CRPS(ensemble_dim='number')},
         evaluate_probabilistic_climatology=True,
         probabilistic_climatology_start_year=2018,
         probabilistic_climatology_end_year=2019,
         probabilistic_climatology_hour_interval=12)})
-  assert fake.calls and fake.calls[0][0] == 'ens_metrics'
+  if fake is not None:
+    assert fake.calls and fake.calls[0][0] == 'ens_metrics'
   hours, days, pc = orc.probabilistic_climatology(tarr['geopotential'], ttimes,
                                                   2018, 2019, 12)
   vt = itimes[:, None] + lead[None, :]
@@ -315,10 +321,11 @@ def test_evaluate_probabilistic_climatology_crps_in_memory(tmp_path):
   want, wd = orc.crps(cf, fd, tg, td, 'number', lat, lon)
   want = want.mean(axis=wd.index('time'))
   res = out['pc']['geopotential']
-  np.testing.assert_allclose(res.values[0], want, rtol=1e-5)
+  np.testing.assert_allclose(res.values[0], want, rtol=crps_rtol)
 
 
-def test_against_analysis_by_valid_and_by_init(tmp_path):
+def case_against_analysis_by_valid_and_by_init(tmp_path, scope, crps_rtol=1e-5,
+                                               det_rtol=2e-6):
   from weatherbench2_b200 import config, evaluation, metrics
   lat, lon = _grid()
   truth, _, _, _ = _truth('2020-01-01', '2020-01-12', 6)
@@ -328,21 +335,21 @@ def test_against_analysis_by_valid_and_by_init(tmp_path):
   fc, farr, _, lead = _forecast('2020-01-02', '2020-01-05', 12, [0, 12, 24],
                                 False)
   f = farr['geopotential']
-  with fake_ctx.installed():
+  with scope():
     out = evaluation.evaluate_in_memory(
         _data_config(fc, truth, tmp_path, False),
         {'an': config.Eval(metrics=mets, against_analysis=True)})
   t = np.repeat(f[:, :1], lead.size, axis=1)
   want, wd = _rmse_time_mean(f, t, dims, lat, lon, 'time')
   np.testing.assert_allclose(out['an']['geopotential'].values[0], want,
-                             rtol=2e-6)
+                             rtol=det_rtol)
   # by-init (evaluation.py:259-293): inits every 12 h, leads every 6 h ->
   # every second lead has an analysis; the last inits lack one -> error unless
   # the evaluated init times stop early enough
   fc, farr, itimes, lead = _forecast('2020-01-02', '2020-01-06', 12,
                                      [0, 6, 12, 18, 24], True)
   f = farr['geopotential']
-  with fake_ctx.installed():
+  with scope():
     with pytest.raises(AssertionError, match='Analysis does not extend'):
       evaluation.evaluate_in_memory(
           _data_config(fc, truth, tmp_path, True),
@@ -358,10 +365,11 @@ def test_against_analysis_by_valid_and_by_init(tmp_path):
   want, wd = _rmse_time_mean(fs, ts, dims, lat, lon, 'time')
   res = out['an']['geopotential']
   assert res.sizes['lead_time'] == 3
-  np.testing.assert_allclose(res.values[0], want, rtol=2e-6)
+  np.testing.assert_allclose(res.values[0], want, rtol=det_rtol)
 
 
-def test_selection_box_levels_suffixes_and_step_thinning(tmp_path):
+def case_selection_box_levels_suffixes_and_step_thinning(tmp_path, scope, crps_rtol=1e-5,
+                                                         det_rtol=2e-6):
   from weatherbench2_b200 import config, evaluation, metrics
   from weatherbench2_b200 import xarray_lite as xl
   lat, lon = _grid(13, 24)
@@ -381,7 +389,7 @@ def test_selection_box_levels_suffixes_and_step_thinning(tmp_path):
                     lat_slice=slice(-45, 60), lon_slice=slice(30, 200),
                     time_slice=slice('2020-01-02', '2020-01-04'))
   dc.pressure_level_suffixes = True
-  with fake_ctx.installed():
+  with scope():
     out = evaluation.evaluate_in_memory(dc, {'det': config.Eval(
         metrics={'mse': metrics.MSE()})})
   # oracle: same box / levels / times; truth thinned 6 h -> 12 h by the
@@ -400,15 +408,29 @@ def test_selection_box_levels_suffixes_and_step_thinning(tmp_path):
   assert res.sizes == {'metric': 1, 'lead_time': 2, 'level': 2}
   np.testing.assert_allclose(
       res.transpose('metric', *[d for d in wd if d != 'time']).values[0],
-      want.mean(axis=wd.index('time')), rtol=2e-6)
+      want.mean(axis=wd.index('time')), rtol=det_rtol)
   # time steps that are not multiples of each other are refused
   odd = truth.isel(time=np.array([0, 1, 2, 4, 8]))
-  with fake_ctx.installed(), pytest.raises(ValueError, match='unique'):
+  with scope(), pytest.raises(ValueError, match='unique'):
     evaluation.evaluate_in_memory(
         _data_config(fc, odd, tmp_path, False),
         {'det': config.Eval(metrics={'mse': metrics.MSE()})})
   # a variable that neither dataset holds is a KeyError, as with xarray
-  with fake_ctx.installed(), pytest.raises(KeyError):
+  with scope(), pytest.raises(KeyError):
     evaluation.evaluate_in_memory(
         _data_config(fc, truth, tmp_path, False, variables=['nope']),
         {'det': config.Eval(metrics={'mse': metrics.MSE()})})
+
+
+CASES = [case_config0_rmse_64x64_plumbing,
+         case_evaluate_climatology_and_persistence_in_memory,
+         case_evaluate_persistence_by_valid_in_memory,
+         case_evaluate_probabilistic_climatology_crps_in_memory,
+         case_against_analysis_by_valid_and_by_init,
+         case_selection_box_levels_suffixes_and_step_thinning]
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: c.__name__[5:])
+def test_in_memory_evaluation_host_logic(case, tmp_path):
+  """The cases above with the NumPy stand-in context (no GPU)."""
+  case(tmp_path, fake_ctx.installed)
