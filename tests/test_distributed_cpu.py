@@ -157,3 +157,65 @@ def test_prefetching_feeder_gives_the_same_result():
   b = wd.evaluate_sharded(forecast, truth, None, loop_fn=_oracle_loop,
                           chunk_size=2, prefetch=2, num_threads=3)
   np.testing.assert_array_equal(a['z'].values, b['z'].values)
+
+
+# ---- the product loop itself (operators -> offset tables -> C-ABI arguments)
+# under gloo, with the NumPy stand-in context of tests/fake_ctx.py ----------------
+def _eval_config():
+  from weatherbench2_b200 import config, metrics, regions as R
+  return config.Eval(
+      metrics={'rmse': metrics.RMSESqrtBeforeTimeAvg(), 'bias': metrics.Bias()},
+      regions={'global': R.SliceRegion(),
+               'tropics': R.SliceRegion(lat_slice=slice(-20, 20)),
+               'extra-tropics': R.ExtraTropicalRegion()})
+
+
+def _product_worker(rank, world, port, prefetch, outdir):
+  import torch.distributed as dist
+  import fake_ctx
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  forecast, truth = _make_data(ninit=5)
+  with fake_ctx.installed() as fake:
+    res = wd.evaluate_sharded(forecast, truth, _eval_config(), prefetch=prefetch)
+  np.save(os.path.join(outdir, f'rank{rank}.npy'), res['z'].values)
+  np.save(os.path.join(outdir, f'calls{rank}.npy'), len(fake.calls))
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('prefetch', [0, 2])
+def test_two_rank_gloo_runs_the_product_loop(tmp_path, prefetch):
+  from oracle import wb2_oracle as orc
+  import fake_ctx
+  world = 2
+  mp.spawn(_product_worker, args=(world, _free_port(), prefetch, str(tmp_path)),
+           nprocs=world, join=True)
+  got = [np.load(tmp_path / f'rank{r}.npy') for r in range(world)]
+  np.testing.assert_array_equal(got[0], got[1])
+  # 5 init-time chunks over 2 ranks: 3 + 2, one K1 pass per chunk for both
+  # metrics and all three regions
+  assert [int(np.load(tmp_path / f'calls{r}.npy')) for r in range(world)] == [
+      3, 2]
+  forecast, truth = _make_data(ninit=5)
+  f = forecast['z'].values
+  vt = forecast['valid_time'].values
+  pos = {t: i for i, t in enumerate(truth['time'].values)}
+  tg = np.stack([np.stack([truth['z'].values[pos[v]] for v in row])
+                 for row in vt])
+  dims = ('time', 'lead_time', 'latitude', 'longitude')
+  lat, lon = forecast['latitude'].values, forecast['longitude'].values
+  regs = [None, orc.SliceRegion(lat_slice=slice(-20, 20)),
+          orc.ExtraTropicalRegion()]
+  for ri, reg in enumerate(regs):
+    want, wdims = orc.rmse_sqrt_before_time_avg(f, dims, tg, dims, lat, lon,
+                                                region=reg)
+    np.testing.assert_allclose(got[0][0, ri], want.mean(axis=wdims.index('time')),
+                               rtol=2e-6)
+    want, wdims = orc.bias(f, dims, tg, dims, lat, lon, region=reg)
+    np.testing.assert_allclose(got[0][1, ri], want.mean(axis=wdims.index('time')),
+                               rtol=2e-6, atol=1e-9)
+  # single process, same loop: identical numbers
+  with fake_ctx.installed():
+    single = wd.evaluate_sharded(forecast, truth, _eval_config())
+  np.testing.assert_allclose(single['z'].values, got[0], rtol=1e-12)
