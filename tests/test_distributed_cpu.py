@@ -219,3 +219,48 @@ def test_two_rank_gloo_runs_the_product_loop(tmp_path, prefetch):
   with fake_ctx.installed():
     single = wd.evaluate_sharded(forecast, truth, _eval_config())
   np.testing.assert_allclose(single['z'].values, got[0], rtol=1e-12)
+
+
+# ---- evaluate_with_beam drop-in == evaluate_in_memory (the reference's own
+# consistency test, weatherbench2/evaluation_test.py:30-128) -----------------------
+def _beam_worker(rank, world, port, by_init, outdir):
+  import torch.distributed as dist
+  import fake_ctx
+  from weatherbench2_b200 import evaluation
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  import test_evaluation_cpu as ev
+  dc, eval_configs = ev.consistency_setup(os.path.join(outdir, 'beam'),
+                                          by_init)
+  chunk_dim = 'init_time' if by_init else 'time'
+  with fake_ctx.installed():
+    out = evaluation.evaluate_with_beam(dc, eval_configs,
+                                        input_chunks={chunk_dim: 2},
+                                        runner='DirectRunner', num_threads=2)
+  for name, ds in out.items():
+    np.save(os.path.join(outdir, f'{name}.rank{rank}.npy'),
+            ds['geopotential'].values)
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('by_init', [True, False])
+def test_in_memory_and_distributed_consistency(tmp_path, by_init):
+  import fake_ctx
+  from weatherbench2_b200 import evaluation
+  world = 2
+  mp.spawn(_beam_worker, args=(world, _free_port(), by_init, str(tmp_path)),
+           nprocs=world, join=True)
+  import test_evaluation_cpu as ev
+  dc, eval_configs = ev.consistency_setup(tmp_path / 'mem', by_init)
+  with fake_ctx.installed():
+    mem = evaluation.evaluate_in_memory(dc, eval_configs)
+  for name in eval_configs:
+    got = [np.load(tmp_path / f'{name}.rank{r}.npy') for r in range(world)]
+    np.testing.assert_array_equal(got[0], got[1])
+    want = mem[name]['geopotential'].values
+    assert got[0].shape == want.shape, name
+    np.testing.assert_allclose(got[0], want, rtol=1e-12, atol=1e-15,
+                               err_msg=name)
+    # rank 0 wrote the file, as evaluate_in_memory does
+    assert (tmp_path / 'beam' / f'{name}.npz').exists()

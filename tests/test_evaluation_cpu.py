@@ -422,12 +422,69 @@ def case_selection_box_levels_suffixes_and_step_thinning(tmp_path, scope, crps_r
         {'det': config.Eval(metrics={'mse': metrics.MSE()})})
 
 
+def consistency_setup(tmp_path, by_init=True):
+  from weatherbench2_b200 import config, metrics, regions as R
+  truth, _, _, _ = _truth('2019-12-20', '2020-02-10', 6)
+  # (by-valid persistence needs every valid time - lead in the time-sliced,
+  # step-thinned truth: evaluation.py:165-193)
+  fc, _, _, _ = _forecast('2020-01-01', '2020-01-08', 12,
+                             [0, 6, 30] if by_init else [0, 12, 36], by_init)
+  clim, _, _ = _climatology()
+  regions = {'global': R.SliceRegion(),
+             'tropics': R.SliceRegion(lat_slice=slice(-20, 20)),
+             'extra-tropics': R.ExtraTropicalRegion()}
+  eval_configs = {
+      'forecast_vs_era': config.Eval(metrics={
+          'rmse': metrics.RMSESqrtBeforeTimeAvg(),
+          'acc': metrics.ACC(climatology=clim)}),
+      'forecast_vs_era_by_region': config.Eval(
+          metrics={'rmse': metrics.RMSESqrtBeforeTimeAvg()}, regions=regions),
+      'forecast_vs_era_temporal': config.Eval(
+          metrics={'rmse': metrics.RMSESqrtBeforeTimeAvg()},
+          temporal_mean=False),
+      'climatology_vs_era': config.Eval(
+          metrics={'mse': metrics.MSE()}, evaluate_climatology=True),
+      'persistence_vs_era': config.Eval(
+          metrics={'mse': metrics.MSE()}, evaluate_persistence=True),
+  }
+  dc = _data_config(fc, truth, tmp_path, by_init, climatology=clim,
+                       time_slice=slice('2020-01-02', '2020-01-06'))
+  return dc, eval_configs
+
+
+def case_in_memory_and_chunked_consistency(tmp_path, scope, crps_rtol=1e-5,
+                                           det_rtol=2e-6):
+  """evaluate_with_beam (chunks of 2 init times through the feeder, slab cache
+  and [sum, count] accumulator; one process) == evaluate_in_memory, the
+  reference's own consistency test (evaluation_test.py:30-128).  The
+  two-rank version runs under gloo in tests/test_distributed_cpu.py."""
+  del crps_rtol, det_rtol
+  from weatherbench2_b200 import evaluation
+  for by_init in (True, False):
+    chunk_dim = 'init_time' if by_init else 'time'
+    dc, eval_configs = consistency_setup(tmp_path / f'mem{by_init}', by_init)
+    with scope():
+      mem = evaluation.evaluate_in_memory(dc, eval_configs)
+    dc, eval_configs = consistency_setup(tmp_path / f'chunked{by_init}',
+                                         by_init)
+    with scope():
+      chunked = evaluation.evaluate_with_beam(
+          dc, eval_configs, input_chunks={chunk_dim: 2}, runner='DirectRunner')
+    for name in eval_configs:
+      got = chunked[name]['geopotential']
+      want = mem[name]['geopotential']
+      assert got.dims == want.dims and got.shape == want.shape, name
+      np.testing.assert_allclose(got.values, want.values, rtol=1e-12,
+                                 atol=1e-15, err_msg=name)
+
+
 CASES = [case_config0_rmse_64x64_plumbing,
          case_evaluate_climatology_and_persistence_in_memory,
          case_evaluate_persistence_by_valid_in_memory,
          case_evaluate_probabilistic_climatology_crps_in_memory,
          case_against_analysis_by_valid_and_by_init,
-         case_selection_box_levels_suffixes_and_step_thinning]
+         case_selection_box_levels_suffixes_and_step_thinning,
+         case_in_memory_and_chunked_consistency]
 
 
 @pytest.mark.parametrize('case', CASES, ids=lambda c: c.__name__[5:])

@@ -107,6 +107,39 @@ class TimeMeanAccumulator:
     return out
 
 
+def _gather_chunks(per_chunk: list, indices: list, chunk_dim: str, world: int,
+                   group=None) -> xl.Dataset:
+  """All ranks' per-chunk results, concatenated along `chunk_dim` in chunk
+  order (the un-reduced output of the reference's pipeline when
+  `temporal_mean=False`).  Variables without `chunk_dim` (it was averaged or
+  never present) are taken from the first chunk."""
+  pairs = list(zip(indices, per_chunk))
+  if world > 1:
+    dist = _dist()
+    payload = [(i, {k: (ds[k].dims, ds[k].values) for k in ds.keys()},
+                {k: (c.dims, c.values) for k, c in ds.coords.items()})
+               for i, ds in pairs]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, payload, group=group)
+    pairs = []
+    for part in gathered:
+      for i, data_vars, coords in part:
+        pairs.append((i, xl.Dataset(data_vars, coords)))
+  pairs.sort(key=lambda p: p[0])
+  if not pairs:
+    return xl.Dataset()
+  parts = [ds for _, ds in pairs]
+  if all(chunk_dim in parts[0][k].dims for k in parts[0].keys()):
+    return xl.concat(parts, chunk_dim)
+  out = xl.Dataset(attrs=parts[0].attrs)
+  for k in parts[0].keys():
+    if chunk_dim in parts[0][k].dims:
+      out[k] = xl.concat([xl.Dataset({k: p[k]}) for p in parts], chunk_dim)[k]
+    else:
+      out[k] = parts[0][k]
+  return out
+
+
 def _truth_for_chunk(truth, fc, chunk_dim, select_truth):
   """Truth of one forecast chunk.  By-valid chunks (`chunk_dim == 'time'`) are
   aligned BY LABEL like the reference's xarray arithmetic -- the truth record
@@ -124,7 +157,8 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
                      chunk_size: int = 1, group=None, device=None,
                      loop_fn: t.Optional[t.Callable] = None,
                      select_truth: t.Optional[t.Callable] = None,
-                     prefetch: int = 0, num_threads: int = 2) -> xl.Dataset:
+                     prefetch: int = 0, num_threads: int = 2,
+                     temporal_mean: bool = True) -> xl.Dataset:
   """Time-mean metric results with the chunks of `chunk_dim` sharded over the
   process group.  Every rank returns the full (identical) result.
 
@@ -139,6 +173,9 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   reader threads (the DatasetToChunks replacement, evaluation.py:693-705), so
   the read of chunk i+1 overlaps the kernels of chunk i and the H2D copies run
   at the PCIe rate.
+  temporal_mean=False (config.Eval.temporal_mean, evaluation.py:733-744): no
+  reduction -- the per-chunk results are gathered from all ranks and
+  concatenated along `chunk_dim` in chunk order.
   """
   from weatherbench2_b200 import evaluation  # pylint: disable=import-outside-toplevel
   dist = _dist()
@@ -170,10 +207,17 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
   else:
     chunks = (forecast.isel({chunk_dim: slice(
         ci * chunk_size, min(n, (ci + 1) * chunk_size))}) for ci in mine)
+  per_chunk = []
   with (cache_scope if cache_scope is not None else contextlib.nullcontext()):
     for fc in chunks:
       tr = _truth_for_chunk(truth, fc, chunk_dim, select_truth)
-      acc.add(loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True))
+      res = loop_fn(fc, tr, eval_config, skipna=skipna, compute_chunk=True)
+      if temporal_mean:
+        acc.add(res)
+      else:
+        per_chunk.append(xl.from_xarray(res))
+  if not temporal_mean:
+    return _gather_chunks(per_chunk, mine, chunk_dim, world, group)
   if not acc.sums:
     # a rank without chunks still has to take part in the collective with the
     # right payload shape: evaluate nothing, contribute zeros

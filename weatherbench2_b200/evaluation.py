@@ -515,17 +515,14 @@ def save_results(results: xl.Dataset, path: str) -> None:
   np.savez(path, **payload, allow_pickle=True)
 
 
-def _evaluate_all_metrics(eval_name: str, eval_config: config.Eval,
-                          data_config: config.Data, skipna: bool):
-  """Evaluate a set of eval metrics in memory (evaluation.py:441-483).
-
-  The climatological, probabilistic-climatological and persistence forecasts
-  the reference materialises with `.sel` (evaluation.py:450-472) are lazily
-  gathered views here: the kernels address the climatology / observation slabs
-  in place."""
-  forecast, truth, climatology = open_forecast_and_truth_datasets(
-      data_config, eval_config)
-  time_dim = 'valid_time' if data_config.by_init else 'time'
+def _baseline_forecast(forecast: xl.Dataset, truth: xl.Dataset, climatology,
+                       eval_config: config.Eval, by_init: bool) -> xl.Dataset:
+  """The forecast config.Eval asks to evaluate (evaluation.py:450-472): the
+  model forecast itself, or a climatological / probabilistic-climatological /
+  persistence forecast of the same shape -- as lazily gathered views (the
+  reference materialises each with `.sel`): the kernels address the
+  climatology / observation slabs in place."""
+  time_dim = 'valid_time' if by_init else 'time'
   if eval_config.evaluate_climatology:
     if climatology is None:
       raise ValueError('evaluate_climatology needs config.Paths.climatology')
@@ -539,14 +536,29 @@ def _evaluate_all_metrics(eval_name: str, eval_config: config.Eval,
                                     time_dim)
   if eval_config.evaluate_persistence:
     forecast = create_persistence_forecast(forecast, truth)
-  if data_config.by_init:
-    truth = select_truth_at_valid_time(truth, forecast)  # evaluation.py:475
-  results = _metric_and_region_loop(forecast, truth, eval_config,
-                                    skipna=skipna)
+  return forecast
+
+
+def _save(results: xl.Dataset, data_config: config.Data, eval_name: str,
+          eval_config: config.Eval) -> None:
   fmt = eval_config.output_format if xl.have_xarray() else 'npz'
   output_path = _get_output_path(data_config, eval_name, fmt)
   save_results(results, output_path)
   logging.info('Logging Saved results to %s', output_path)
+
+
+def _evaluate_all_metrics(eval_name: str, eval_config: config.Eval,
+                          data_config: config.Data, skipna: bool):
+  """Evaluate a set of eval metrics in memory (evaluation.py:441-483)."""
+  forecast, truth, climatology = open_forecast_and_truth_datasets(
+      data_config, eval_config)
+  forecast = _baseline_forecast(forecast, truth, climatology, eval_config,
+                                data_config.by_init)
+  if data_config.by_init:
+    truth = select_truth_at_valid_time(truth, forecast)  # evaluation.py:475
+  results = _metric_and_region_loop(forecast, truth, eval_config,
+                                    skipna=skipna)
+  _save(results, data_config, eval_name, eval_config)
   return results
 
 
@@ -559,3 +571,73 @@ def evaluate_in_memory(data_config: config.Data,
     out[eval_name] = _evaluate_all_metrics(eval_name, eval_config, data_config,
                                            skipna=skipna)
   return out
+
+
+def evaluate_distributed(data_config: config.Data, eval_configs: dict, *,
+                         input_chunks: t.Optional[t.Mapping[str, int]] = None,
+                         num_threads: t.Optional[int] = None,
+                         skipna: bool = False, prefetch: int = 2, group=None,
+                         device=None) -> dict:
+  """The chunked, multi-GPU evaluation: what `evaluate_with_beam` is to the
+  reference (evaluation.py:556-828), on a `torch.distributed` process group
+  with one process per GPU.
+
+  For every config.Eval the datasets are opened and the baseline forecast is
+  set up exactly as in `_evaluate_all_metrics`; chunks of
+  `input_chunks['init_time']` (by-init) or `input_chunks['time']` (by-valid)
+  time steps are sharded over the ranks (distributed.evaluate_sharded: pinned
+  chunk feeder with `num_threads` readers, slab cache, one all-reduce of
+  [sum, count] for the temporal mean -- or a gather of the per-chunk results
+  when `temporal_mean=False`).  Other entries of `input_chunks` (lead_time,
+  level, ...) are ignored: a chunk always holds all leads / levels, which the
+  kernels take in one launch.  Every rank returns {eval_name: results}; rank
+  0 writes the result files.  Without a process group it runs on one GPU.
+  """
+  from weatherbench2_b200 import distributed  # pylint: disable=import-outside-toplevel
+  chunk_dim = 'init_time' if data_config.by_init else 'time'
+  chunk_size = int((input_chunks or {}).get(chunk_dim, 1))
+  if chunk_size < 1:  # xarray-beam's -1 = "the whole dimension in one chunk"
+    chunk_size = None
+  import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+  rank = dist.get_rank(group) if (dist.is_available() and
+                                  dist.is_initialized()) else 0
+  out = {}
+  for eval_name, eval_config in eval_configs.items():
+    forecast, truth, climatology = open_forecast_and_truth_datasets(
+        data_config, eval_config)
+    forecast = _baseline_forecast(forecast, truth, climatology, eval_config,
+                                  data_config.by_init)
+    baseline = (eval_config.evaluate_climatology or
+                eval_config.evaluate_probabilistic_climatology or
+                eval_config.evaluate_persistence)
+    results = distributed.evaluate_sharded(
+        forecast, truth, eval_config, skipna=skipna, chunk_dim=chunk_dim,
+        chunk_size=chunk_size or forecast.sizes[chunk_dim], group=group,
+        device=device,
+        # a baseline forecast is a view of resident climatology / observation
+        # slabs: nothing to read ahead (a feeder would copy it chunk by chunk)
+        prefetch=0 if baseline else prefetch, num_threads=num_threads or 2,
+        temporal_mean=bool(eval_config.temporal_mean))
+    if rank == 0:
+      _save(results, data_config, eval_name, eval_config)
+    out[eval_name] = results
+  return out
+
+
+def evaluate_with_beam(data_config: config.Data, eval_configs: dict, *,
+                       input_chunks: t.Mapping[str, int],
+                       runner: t.Optional[str] = None,
+                       fanout: t.Optional[int] = None,
+                       shuffle_before_temporal_mean: bool = False,
+                       num_threads: t.Optional[int] = None,
+                       argv: t.Optional[list] = None,
+                       skipna: bool = False) -> dict:
+  """Drop-in for callers of the reference's `evaluate_with_beam`
+  (evaluation.py:758-828; `scripts/evaluate.py`): same arguments, same result
+  files, run by `evaluate_distributed`.  `runner`, `fanout`, `argv` and
+  `shuffle_before_temporal_mean` steer the Beam runner and have no meaning
+  here; they are accepted and ignored."""
+  del runner, fanout, shuffle_before_temporal_mean, argv
+  return evaluate_distributed(data_config, eval_configs,
+                              input_chunks=input_chunks,
+                              num_threads=num_threads, skipna=skipna)

@@ -229,6 +229,11 @@ class DataArray:
       sl = [slice(None)] * data.ndim
       sl[ax] = k
       data = data[tuple(sl)]
+    coords = self._isel_coords(key, drop)
+    return DataArray(data, tuple(new_dims), coords, self.name, self.attrs)
+
+  def _isel_coords(self, key, drop=False) -> dict:
+    """Coordinates after indexing dimension i of `self.dims` with key[i]."""
     coords = {}
     for name, c in self.coords.items():
       ck = tuple(key[self.dims.index(d)] for d in c.dims)
@@ -245,7 +250,7 @@ class DataArray:
           isinstance(kk, numbers.Integral) for kk in ck):
         continue
       coords[name] = Coord(cd, v, c.attrs)
-    return DataArray(data, tuple(new_dims), coords, self.name, self.attrs)
+    return coords
 
   def _label_indexer(self, dim, label, method=None):
     if dim not in self.coords:
@@ -1009,6 +1014,44 @@ class LazyGather(DataArray):
   @property
   def dtype(self):
     return self._source.dtype
+
+  def isel(self, indexers=None, drop=False, **kw) -> 'DataArray':
+    """Slices / index arrays keep the view lazy: a looked-up dimension
+    restricts the position tables, any other one the source (chunking a
+    climatological or persistence forecast along init_time must not
+    materialise the forecast-sized copy).  Integer indexers fall back to the
+    materialised array."""
+    idx = dict(indexers or {}, **kw)
+    norm = {}
+    for d, k in idx.items():
+      if d not in self.dims:
+        continue
+      if isinstance(k, DataArray):
+        k = k.values
+      if isinstance(k, (list, tuple)):
+        k = np.asarray(k)
+      if not (isinstance(k, slice) or (isinstance(k, np.ndarray) and
+                                       k.ndim == 1)):
+        return DataArray(self.values, self.dims, self.coords, self.name,
+                         self.attrs).isel(idx, drop=drop)
+      norm[d] = k
+    source, maps = self._source, dict(self._index_maps)
+    for d, k in norm.items():
+      looked_up = False
+      for sd, (tdims, pos) in list(maps.items()):
+        if d in tdims:
+          sl = [slice(None)] * pos.ndim
+          sl[tdims.index(d)] = k
+          maps[sd] = (tdims, pos[tuple(sl)])
+          looked_up = True
+      if not looked_up:
+        source = source.isel({d: k})
+    key = [norm.get(d, slice(None)) for d in self.dims]
+    coords = self._isel_coords(key, drop)
+    out = LazyGather(source, maps)
+    out.coords = coords
+    out.name, out.attrs = self.name, dict(self.attrs)
+    return out
 
 
 def align_inner(a: DataArray, b: DataArray):
