@@ -176,3 +176,49 @@ def test_upload_gathered_packs_only_referenced_slabs_and_keeps_members_plain():
   assert m_ == nm and stride == table[tuple(
       1 if d == 'realization' else 0 for d in dims)]
   assert 'realization' not in rest.outer_dims
+
+
+@pytest.mark.parametrize('hist,expected,desired', [
+    # weatherbench2/metrics_test.py:701-779 (known answers)
+    ([0.2, 0.1, 0.7], [0.1, 1.0], [1 / 3, 1.0]),
+    ([0.2, 0.0, 0.1, 0.1, 0.6], [0.1, 0.2, 1.0], [1 / 5, 3 / 5, 1]),
+    ([0.1, 0.1, 0.5, 0.3], [0.6, 1.0], [1 / 2, 1.0]),
+    ([0.1, 0.1, 0.3, 0.2, 0.0, 0.3], [0.5, 0.6, 1.0], [1 / 3, 2 / 3, 1]),
+])
+def test_central_reliability_known_answers(hist, expected, desired):
+  from weatherbench2_b200 import metrics
+  from weatherbench2_b200 import xarray_lite as xl
+  ds = xl.Dataset({'temperature': (('bins',), np.array(hist))},
+                  {'bins': np.arange(len(hist))})
+  rel = metrics.central_reliability(ds)
+  da = rel['temperature']
+  assert da.dims == ('desired_prob',)
+  np.testing.assert_allclose(da.values, expected, rtol=1e-12)
+  np.testing.assert_allclose(da.coords['desired_prob'].values, desired,
+                             rtol=1e-12)
+  np.testing.assert_array_equal(da.coords['prob_index'].values,
+                                np.arange(len(expected)))
+
+
+@pytest.mark.parametrize('n_bins', [3, 4, 10, 11])
+def test_central_reliability_of_a_calibrated_histogram(n_bins):
+  """metrics_test.py:666-699: expected == desired probabilities; extra
+  dimensions ride along; fewer than 3 bins is an error (:655-664)."""
+  from weatherbench2_b200 import metrics
+  from weatherbench2_b200 import xarray_lite as xl
+  h = np.ones((2, n_bins)) / n_bins
+  ds = xl.Dataset({'temperature': (('level', 'bins'), h)},
+                  {'bins': np.arange(n_bins), 'level': [500, 850]})
+  rel = metrics.central_reliability(ds)['temperature']
+  assert rel.sizes['desired_prob'] == n_bins // 2 + n_bins % 2
+  unnorm = np.ones(n_bins // 2)
+  if n_bins % 2:
+    unnorm = np.concatenate(([0.5], unnorm))
+  want = np.cumsum(unnorm) / unnorm.sum()
+  got = rel.transpose('level', 'desired_prob').values
+  np.testing.assert_allclose(got, np.stack([want, want]), rtol=1e-12)
+  np.testing.assert_allclose(rel.coords['desired_prob'].values, want,
+                             rtol=1e-12)
+  with pytest.raises(ValueError, match='Too few bins'):
+    metrics.central_reliability(xl.Dataset(
+        {'temperature': (('bins',), np.ones(2) / 2)}, {'bins': np.arange(2)}))

@@ -121,3 +121,63 @@ def _run(ctx, x_op, t_op, ens_dim, nbins, reduce_dim, random_ties, seed):
   finally:
     for p in staged:
       ctx.free(p)
+
+
+def central_reliability(hist):
+  """Reliability diagram for central histogram probabilities
+  (weatherbench2/metrics.py:2045-2126), computed on an already reduced rank
+  histogram (a handful of numbers per variable -- result assembly like the
+  final `sum / weight_sum`, not kernel work).
+
+  For N bins the probability that truth was less extreme than the central
+  2(k+1) - N%2 bins, k = 0 .. N//2 - 1 + N%2, indexed by the probability a
+  perfectly calibrated forecast would give, `desired_prob` (with the integer
+  `prob_index` as a coordinate along it).
+  """
+  native = xl.is_native_xarray(hist)
+  ds = xl.from_xarray(hist)
+  single = isinstance(ds, xl.DataArray)
+  if single:
+    ds = xl.Dataset({ds.name or '_': ds})
+  n_bins = ds.sizes['bins']
+  if n_bins < 3:
+    raise ValueError(f'Too few bins. {n_bins=} but should be >= 3')
+  half, odd = n_bins // 2, n_bins % 2
+  # label-based like the reference's .sel (bins are 0 .. N-1)
+  bins = np.asarray(ds.coords['bins'].values) if 'bins' in ds.coords else (
+      np.arange(n_bins))
+  left_idx = xl.label_slice_indices(bins, slice(None, half - 1))
+  right_idx = xl.label_slice_indices(bins, slice(half + odd, None))
+  desired = np.ones(left_idx.size)
+  if odd:
+    desired = np.concatenate(([0.5], desired))
+  desired = np.cumsum(desired)
+  desired = desired / desired[-1]
+  out = xl.Dataset(attrs=ds.attrs)
+  for name in ds.keys():
+    da = ds[name]
+    if 'bins' not in da.dims:
+      out[name] = da
+      continue
+    ax = da.dims.index('bins')
+    h = np.moveaxis(np.asarray(da.values), ax, -1)
+    # cumulative sum from the centre outwards: left half reversed + right half
+    probs = np.cumsum(h[..., left_idx[::-1]] + h[..., right_idx], axis=-1)
+    other = tuple(d for d in da.dims if d != 'bins')
+    if odd:
+      center = h[..., int(xl._lookup(bins, np.array([half]))[0])]  # pylint: disable=protected-access
+      probs = np.concatenate([center[..., None], center[..., None] + probs],
+                             axis=-1)
+      # xr.concat puts the expanded prob_index dimension first
+      data, dims = np.moveaxis(probs, -1, 0), ('desired_prob',) + other
+    else:
+      data = np.moveaxis(probs, -1, ax)
+      dims = da.dims[:ax] + ('desired_prob',) + da.dims[ax + 1:]
+    coords = {k: c for k, c in da.coords.items() if 'bins' not in c.dims}
+    coords['desired_prob'] = xl.Coord(('desired_prob',), desired)
+    coords['prob_index'] = xl.Coord(('desired_prob',), np.arange(desired.size))
+    out[name] = xl.DataArray(data, dims, coords, name, da.attrs)
+  if single:
+    result = out[list(out.keys())[0]]
+    return xl.to_xarray(xl.Dataset({'_': result}))['_'] if native else result
+  return xl.to_xarray(out) if native else out

@@ -556,7 +556,7 @@ from weatherbench2_b200._ensemble import (  # noqa: E402  pylint: disable=wrong-
     SpatialEnsembleVariance, DebiasedSpatialEnsembleMeanMSE, _get_n_ensemble)
 # SEEPS (precipitation categories) lives in _seeps.py.
 from weatherbench2_b200._seeps import SEEPS, SpatialSEEPS  # noqa: E402  pylint: disable=wrong-import-position
-from weatherbench2_b200._rank_hist import RankHistogram  # noqa: E402  pylint: disable=wrong-import-position
+from weatherbench2_b200._rank_hist import RankHistogram, central_reliability  # noqa: E402  pylint: disable=wrong-import-position
 # Gaussian-forecast and threshold metrics live in _thresholded.py.
 from weatherbench2_b200._thresholded import (  # noqa: E402  pylint: disable=wrong-import-position
     DebiasedEnsembleBrierScore, EnsembleBrierScore, EnsembleIgnoranceScore,
