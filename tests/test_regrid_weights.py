@@ -92,3 +92,37 @@ def test_grid_validation_and_hash():
   g1 = rg.Grid.from_degrees(np.arange(4) * 90.0, np.array([-90.0, 0.0, 90.0]))
   g2 = rg.Grid.from_degrees(np.arange(4) * 90.0, np.array([-90.0, 0.0, 90.0]))
   assert g1 == g2 and hash(g1) == hash(g2) and g1.shape == (4, 3)
+
+
+def test_grid_node_generators_and_coverage_check():
+  """regridding.py:43-114: the helpers scripts/regrid.py builds target grids
+  with."""
+  from weatherbench2_b200 import regridding as rg
+  lat = rg.latitude_values(rg.LatitudeSpacing.EQUIANGULAR_WITH_POLES, 121)
+  np.testing.assert_allclose(lat, np.linspace(-90, 90, 121))
+  lat = rg.latitude_values(rg.LatitudeSpacing.EQUIANGULAR_WITHOUT_POLES, 32)
+  np.testing.assert_allclose(lat, -90 + (np.arange(32) + 0.5) * 180 / 32)
+  with pytest.raises(ValueError, match='Unhandled'):
+    rg.latitude_values(rg.LatitudeSpacing.CUSTOM, 10)
+  lon = rg.longitude_values(rg.LongitudeScheme.START_AT_ZERO, 240)
+  np.testing.assert_allclose(lon, np.arange(240) * 1.5)
+  lon = rg.longitude_values(rg.LongitudeScheme.CENTER_AT_ZERO, 64)
+  np.testing.assert_allclose(lon, -180 + (np.arange(64) + 0.5) * 360 / 64)
+  assert lon[0] == -lon[-1]
+  # the generated axes feed Grid / the weight builders directly
+  grid = rg.Grid(longitudes=rg.longitude_values(
+      rg.LongitudeScheme.START_AT_ZERO, 8), latitudes=rg.latitude_values(
+          rg.LatitudeSpacing.EQUIANGULAR_WITH_POLES, 5), periodic=True,
+                 includes_poles=True)
+  assert grid.shape == (8, 5)
+  ok_lat = np.linspace(-90, 90, 19)
+  rg._check_global_coverage(np.arange(0, 360.5, 10.0), ok_lat, 0.5)
+  rg._check_global_coverage(np.arange(-180, 180.5, 10.0), ok_lat, 0.5)
+  with pytest.raises(ValueError, match='min latitude'):
+    rg._check_global_coverage(np.arange(0, 361, 10.0), ok_lat[1:], 0.5)
+  with pytest.raises(ValueError, match='max latitude'):
+    rg._check_global_coverage(np.arange(0, 361, 10.0), ok_lat[:-1], 0.5)
+  with pytest.raises(ValueError, match='min longitude'):
+    rg._check_global_coverage(np.arange(10, 361, 10.0), ok_lat, 0.5)
+  with pytest.raises(ValueError, match='max longitude'):
+    rg._check_global_coverage(np.arange(0, 350, 10.0), ok_lat, 0.5)

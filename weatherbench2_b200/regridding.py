@@ -12,6 +12,7 @@ NumPy inputs are streamed through double-buffered device staging
 from __future__ import annotations
 
 import dataclasses
+import enum
 import functools
 from typing import Optional
 
@@ -27,6 +28,69 @@ def _assert_increasing(x: np.ndarray) -> None:
   # regridding.py:297-299
   if not (np.diff(x) > 0).all():
     raise ValueError(f'array is not increasing: {x}')
+
+
+class LongitudeScheme(enum.Enum):
+  """Where a global longitude axis starts (regridding.py:43-48)."""
+  START_AT_ZERO = enum.auto()   # 0, d, 2d, ..., 360 - d
+  CENTER_AT_ZERO = enum.auto()  # -180 + d/2, ..., 180 - d/2
+
+
+class LatitudeSpacing(enum.Enum):
+  """Latitude node placement (regridding.py:51-54)."""
+  EQUIANGULAR_WITH_POLES = enum.auto()
+  EQUIANGULAR_WITHOUT_POLES = enum.auto()
+  CUSTOM = enum.auto()  # e.g. Gaussian grids: nodes are given, not generated
+
+
+def latitude_values(latitude_spacing: LatitudeSpacing, num: int) -> np.ndarray:
+  """`num` equiangular latitudes, pole to pole or cell-centred
+  (regridding.py:57-67)."""
+  if latitude_spacing == LatitudeSpacing.EQUIANGULAR_WITH_POLES:
+    edge = 90.0
+  elif latitude_spacing == LatitudeSpacing.EQUIANGULAR_WITHOUT_POLES:
+    edge = 90.0 - 90.0 / num  # half a cell inside the poles
+  else:
+    raise ValueError(f'Unhandled {latitude_spacing=}')
+  return np.linspace(-edge, edge, num=num)
+
+
+def longitude_values(longitude_scheme: LongitudeScheme, num: int) -> np.ndarray:
+  """`num` equally spaced longitudes covering the circle once
+  (regridding.py:70-82)."""
+  step = 360 / num
+  if longitude_scheme == LongitudeScheme.START_AT_ZERO:
+    first = 0.0
+  elif longitude_scheme == LongitudeScheme.CENTER_AT_ZERO:
+    first = -180 + step / 2
+  else:
+    raise ValueError(f'Unhandled {longitude_scheme=}')
+  return np.linspace(first, first + 360 - step, num=num)
+
+
+def _check_global_coverage(longitudes: np.ndarray, latitudes: np.ndarray,
+                           tolerance: float) -> None:
+  """Raises unless the nodes span the globe to within `tolerance` degrees:
+  latitude -90 .. 90 and longitude 0 .. 360 or -180 .. 180
+  (regridding.py:88-114)."""
+  lo_lat, hi_lat = float(np.min(latitudes)), float(np.max(latitudes))
+  lo_lon, hi_lon = float(np.min(longitudes)), float(np.max(longitudes))
+
+  def near(value, *targets):
+    return any(abs(value - x) < tolerance for x in targets)
+
+  if not near(lo_lat, -90):
+    raise ValueError(
+        f'min latitude must be within ±{tolerance} of -90, found {lo_lat}')
+  if not near(hi_lat, 90):
+    raise ValueError(
+        f'max latitude must be within ±{tolerance} of 90, found {hi_lat}')
+  if not near(lo_lon, 0, -180):
+    raise ValueError(f'min longitude must be within ±{tolerance} of 0 or -180, '
+                     f'found {lo_lon}')
+  if not near(hi_lon, 360, 180):
+    raise ValueError(f'max longitude must be within ±{tolerance} of 360 or '
+                     f'+180, found {hi_lon}')
 
 
 @dataclasses.dataclass(frozen=True)
