@@ -27,14 +27,15 @@ def _view(addr: int, n: int, dtype) -> np.ndarray:
   return np.frombuffer(buf, dtype=dtype, count=n)
 
 
-def _slab(base: int, off: int, w: _lib.WeightSpec, dtype) -> np.ndarray:
+def _slab(base: int, off: int, w: _lib.WeightSpec, dtype,
+          native: bool = False) -> np.ndarray:
   es = np.dtype(dtype).itemsize
   span = (w.nrow - 1) * w.row_stride + w.ncol
   flat = _view(base + int(off) * es, span, dtype)
   rows = np.lib.stride_tricks.as_strided(
       flat, shape=(w.nrow, w.ncol), strides=(w.row_stride * es, es),
       writeable=False)
-  return rows.astype(np.float64)
+  return rows.copy() if native else rows.astype(np.float64)
 
 
 class FakeContext:
@@ -67,6 +68,24 @@ class FakeContext:
 
   def synchronize(self) -> None:
     pass
+
+  @property
+  def launch_count(self) -> int:
+    """Kernel launches the real library makes for the calls so far (the GPU
+    tests assert 'ONE pass serves all metrics / regions' through it): reduction
+    entries = main kernel + finalize, the threshold entry passes of 4 / 2 / 1
+    thresholds + finalize, map entries one kernel."""
+    n = 0
+    for call in self.calls:
+      if call[0] in ('det_metrics', 'det_metrics_vector', 'ens_metrics',
+                     'energy_score', 'gaussian_metrics'):
+        n += 2
+      elif call[0] == 'ens_threshold_metrics':
+        nq = call[2]  # passes of 4, then 2, then 1 thresholds; + finalize
+        n += nq // 4 + (nq % 4 >= 2) + nq % 2 + 1
+      else:
+        n += 1
+    return n
 
   def slab_cache(self, nbytes=None):
     return contextlib.nullcontext()
@@ -110,7 +129,8 @@ class FakeContext:
     for i in range(off_f.size):
       fs = _slab(f, off_f[i], weights, dt)
       ts = _slab(t, off_t[i], weights, dt)
-      d = fs - ts
+      with np.errstate(invalid='ignore'):  # inf - inf in masked-out cells
+        d = fs - ts
       vals = [d * d, np.abs(d), d]
       if c:
         cs = _slab(c, off_c[i], weights, dt)
@@ -136,36 +156,12 @@ class FakeContext:
                   weights, skipna, out):
     self.calls.append(('ens_metrics', int(off_x.size), weights.nregion))
     dt = np.float32 if dtype == _lib.F32 else np.float64
-    es = np.dtype(dt).itemsize
     W = self._weights(weights)
     M = int(nmember)
     res = np.zeros((off_x.size, weights.nregion, _lib.ENS_NSTAT))
-    mean_fn = np.nanmean if skipna else np.mean
     for i in range(off_x.size):
-      xs = np.stack([_slab(x + m * member_stride * es, off_x[i], weights, dt)
-                     for m in range(M)])
-      ts = _slab(t, off_t[i], weights, dt)
-      with np.errstate(invalid='ignore'), _quiet():
-        skill = mean_fn(np.abs(ts[None] - xs), axis=0)
-        if M < 2:
-          spread = np.zeros_like(ts)
-        else:
-          order = np.sort(xs, axis=0)  # NaN last, like np.argsort
-          if skipna:
-            n = (~np.isnan(xs)).sum(axis=0).astype(np.float64)
-            rank = np.arange(1, M + 1, dtype=np.float64)[:, None, None]
-            spread = 2.0 * np.nansum((2 * rank - M - 1) * order, axis=0) / np.where(
-                n > 0, n, np.nan) / (M - 1)
-          else:
-            rank = np.arange(1, M + 1, dtype=np.float64)[:, None, None]
-            spread = 2.0 * ((2 * rank - M - 1) * order).mean(axis=0) / (M - 1)
-        xbar = mean_fn(xs, axis=0)
-        mse = (ts - xbar) ** 2
-        if M > 1:
-          var = (np.nanvar if skipna else np.var)(xs, axis=0, ddof=1)
-        else:
-          var = np.full_like(ts, np.nan)
-        deb = mse - var / M
+      skill, spread, mse, var, deb = self._ens_point(
+          x, t, dt, M, member_stride, off_x[i], off_t[i], weights, skipna)
       for r in range(weights.nregion):
         for k, v in enumerate([skill, spread, mse, var, deb]):
           s, ws = self._wsum(W[r], v, skipna, weights.zero_skip)
@@ -173,10 +169,216 @@ class FakeContext:
           res[i, r, 5 + k] = ws
     _view(out, res.size, np.float64)[...] = res.reshape(-1)
 
+  @staticmethod
+  def _ens_point(x, t, dt, M, member_stride, off_x, off_t, geometry, skipna):
+    """The five point-wise statistics of WB2_ENS_NSTAT's list."""
+    es = np.dtype(dt).itemsize
+    mean_fn = np.nanmean if skipna else np.mean
+    xs = np.stack([_slab(x + m * member_stride * es, off_x, geometry, dt)
+                   for m in range(M)])
+    ts = _slab(t, off_t, geometry, dt)
+    with np.errstate(invalid='ignore'), _quiet():
+      skill = mean_fn(np.abs(ts[None] - xs), axis=0)
+      if M < 2:
+        spread = np.zeros_like(ts)
+      else:
+        order = np.sort(xs, axis=0)  # NaN last, like np.argsort
+        rank = np.arange(1, M + 1, dtype=np.float64)[:, None, None]
+        if skipna:
+          n = (~np.isnan(xs)).sum(axis=0).astype(np.float64)
+          spread = 2.0 * np.nansum((2 * rank - M - 1) * order, axis=0) / np.where(
+              n > 0, n, np.nan) / (M - 1)
+        else:
+          spread = 2.0 * ((2 * rank - M - 1) * order).mean(axis=0) / (M - 1)
+      xbar = mean_fn(xs, axis=0)
+      mse = (ts - xbar) ** 2
+      if M > 1:
+        var = (np.nanvar if skipna else np.var)(xs, axis=0, ddof=1)
+      else:
+        var = np.full_like(ts, np.nan)
+      deb = mse - var / M
+    return [skill, spread, mse, var, deb]
+
   def ens_metrics_host(self, x, t, nmember, member_stride, off_x, off_t,
                        weights, skipna, out):
     self.ens_metrics(x, t, _lib.F32, nmember, member_stride, off_x, off_t,
                      weights, skipna, out)
+
+  def det_metrics_vector(self, fu, fv, tu, tv, dtype, off_fu, off_fv, off_tu,
+                         off_tv, weights, skipna, out):
+    self.calls.append(('det_metrics_vector', int(off_fu.size), weights.nregion))
+    dt = np.float32 if dtype == _lib.F32 else np.float64
+    W = self._weights(weights)
+    res = np.zeros((off_fu.size, weights.nregion, _lib.DET_NSTAT))
+    for i in range(off_fu.size):
+      du = _slab(fu, off_fu[i], weights, dt) - _slab(tu, off_tu[i], weights, dt)
+      dv = _slab(fv, off_fv[i], weights, dt) - _slab(tv, off_tv[i], weights, dt)
+      for r in range(weights.nregion):
+        res[i, r, 0], res[i, r, 6] = self._wsum(W[r], du * du + dv * dv, skipna,
+                                                weights.zero_skip)
+    _view(out, res.size, np.float64)[...] = res.reshape(-1)
+
+  # -- K3 -----------------------------------------------------------------------
+  def energy_score(self, x, t, dtype, nmember, member_stride, off_x, off_t,
+                   weights, out):
+    self.calls.append(('energy_score', int(off_x.size), weights.nregion))
+    dt = np.float32 if dtype == _lib.F32 else np.float64
+    es = np.dtype(dt).itemsize
+    W = self._weights(weights)
+    M = int(nmember)
+    res = np.zeros((off_x.size, weights.nregion, 4, M))
+    for i in range(off_x.size):
+      xs = [_slab(x + m * member_stride * es, off_x[i], weights, dt)
+            for m in range(M)]
+      ts = _slab(t, off_t[i], weights, dt)
+      for r in range(weights.nregion):
+        for m in range(M):
+          res[i, r, 0, m], res[i, r, 2, m] = self._wsum(
+              W[r], (xs[m] - ts) ** 2, False, weights.zero_skip)
+          if m < M - 1:
+            res[i, r, 1, m], res[i, r, 3, m] = self._wsum(
+                W[r], (xs[m] - xs[m + 1]) ** 2, False, weights.zero_skip)
+    _view(out, res.size, np.float64)[...] = res.reshape(-1)
+
+  # -- K6 / K6e -----------------------------------------------------------------
+  @staticmethod
+  def _geometry(nrow, ncol, row_stride):
+    return _lib.WeightSpec(nrow, ncol, np.ones((1, nrow)), [0, ncol],
+                           np.ones((1, 1)), row_stride=row_stride)
+
+  def det_maps(self, f, t, dtype, stat, nout, ngroup, off_f, off_t, nrow, ncol,
+               row_stride, skipna, out):
+    self.calls.append(('det_maps', int(nout), int(ngroup)))
+    dt = np.float32 if dtype == _lib.F32 else np.float64
+    g = self._geometry(nrow, ncol, row_stride)
+    res = np.empty((nout, nrow, ncol), dtype=dt)
+    for j in range(nout):
+      terms = []
+      for k in range(ngroup):
+        # the kernel forms the point-wise term in the input precision
+        d = (_slab(f, off_f[j * ngroup + k], g, dt, native=True) -
+             _slab(t, off_t[j * ngroup + k], g, dt, native=True))
+        terms.append([d, d * d, np.abs(d)][stat].astype(np.float64))
+      with _quiet():
+        res[j] = (np.nanmean if skipna else np.mean)(np.stack(terms), axis=0)
+    _view(out, res.size, dt)[...] = res.reshape(-1)
+
+  def ens_maps(self, x, t, dtype, nmember, member_stride, nout, ngroup, off_x,
+               off_t, nrow, ncol, row_stride, stat_mask, skipna, out):
+    self.calls.append(('ens_maps', int(nout), int(ngroup), int(stat_mask)))
+    dt = np.float32 if dtype == _lib.F32 else np.float64
+    g = self._geometry(nrow, ncol, row_stride)
+    sel = [b for b in range(6) if stat_mask >> b & 1]
+    res = np.empty((len(sel), nout, nrow, ncol), dtype=np.float32)
+    for j in range(nout):
+      terms = []
+      for k in range(ngroup):
+        point = self._ens_point(x, t, dt, nmember, member_stride,
+                                off_x[j * ngroup + k], off_t[j * ngroup + k], g,
+                                skipna)
+        point.append(point[0] - 0.5 * point[1])
+        terms.append(np.stack([point[b] for b in sel]))
+      with _quiet():
+        res[:, j] = (np.nanmean if skipna else np.mean)(np.stack(terms), axis=0)
+    _view(out, res.size, np.float32)[...] = res.reshape(-1)
+
+  # -- K7: threshold / Gaussian metrics -------------------------------------------
+  # (point-wise scores from the oracle: this stand-in checks the operand
+  # staging, the threshold tables and the result assembly, not the arithmetic)
+  @staticmethod
+  def _threshold_fields(nthreshold, thr_a, off_a, thr_b, off_b, z, field, nfield,
+                        g):
+    out = []
+    for k in range(nthreshold):
+      if thr_b:
+        mean = _slab(thr_a, off_a[field], g, np.float32)
+        std = _slab(thr_b, off_b[field], g, np.float32)
+        out.append(mean + np.float64(z[k]) * std)
+      else:
+        out.append(_slab(thr_a, np.asarray(off_a).reshape(
+            nthreshold, nfield)[k, field], g, np.float32))
+    return out
+
+  @staticmethod
+  def _ens_threshold_point(xs, ts, thr, skipna):
+    from oracle import wb2_oracle as orc  # pylint: disable=import-outside-toplevel
+    with np.errstate(invalid='ignore', divide='ignore'), _quiet():
+      return [orc.ens_brier_pointwise(xs, ts, thr, 0, False, skipna),
+              orc.ens_brier_pointwise(xs, ts, thr, 0, True, skipna),
+              orc.ens_ignorance_pointwise(xs, ts, thr, 0, skipna),
+              orc.ens_rps_part_pointwise(xs, ts, thr, 0, skipna)]
+
+  def ens_threshold_metrics(self, x, t, nmember, member_stride, off_x, off_t,
+                            nthreshold, thr_a, off_a, thr_b, off_b, z, weights,
+                            skipna, out):
+    self.calls.append(('ens_threshold_metrics', int(off_x.size), nthreshold))
+    W = self._weights(weights)
+    nfield = off_x.size
+    res = np.zeros((nfield, nthreshold, weights.nregion, 8))
+    for i in range(nfield):
+      xs = np.stack([_slab(x + m * member_stride * 4, off_x[i], weights,
+                           np.float32) for m in range(nmember)])
+      ts = _slab(t, off_t[i], weights, np.float32)
+      thrs = self._threshold_fields(nthreshold, thr_a, off_a, thr_b, off_b, z,
+                                    i, nfield, weights)
+      for k, thr in enumerate(thrs):
+        for r in range(weights.nregion):
+          for q, v in enumerate(self._ens_threshold_point(xs, ts, thr, skipna)):
+            res[i, k, r, q], res[i, k, r, 4 + q] = self._wsum(
+                W[r], v, skipna, weights.zero_skip)
+    _view(out, res.size, np.float64)[...] = res.reshape(-1)
+
+  def ens_threshold_maps(self, x, t, nmember, member_stride, nout, ngroup,
+                         off_x, off_t, nthreshold, thr_a, off_a, thr_b, off_b,
+                         z, nrow, ncol, row_stride, stat, skipna, out):
+    self.calls.append(('ens_threshold_maps', int(nout), int(ngroup), stat))
+    g = self._geometry(nrow, ncol, row_stride)
+    nfield = nout * ngroup
+    res = np.empty((nthreshold, nout, nrow, ncol), dtype=np.float32)
+    for j in range(nout):
+      terms = [[] for _ in range(nthreshold)]
+      for q in range(ngroup):
+        i = j * ngroup + q
+        xs = np.stack([_slab(x + m * member_stride * 4, off_x[i], g, np.float32)
+                       for m in range(nmember)])
+        ts = _slab(t, off_t[i], g, np.float32)
+        thrs = self._threshold_fields(nthreshold, thr_a, off_a, thr_b, off_b,
+                                      z, i, nfield, g)
+        for k, thr in enumerate(thrs):
+          terms[k].append(self._ens_threshold_point(xs, ts, thr, skipna)[stat])
+      with _quiet():
+        for k in range(nthreshold):
+          res[k, j] = (np.nanmean if skipna else np.mean)(np.stack(terms[k]),
+                                                          axis=0)
+    _view(out, res.size, np.float32)[...] = res.reshape(-1)
+
+  def gaussian_metrics(self, mean, std, t, off_mean, off_std, off_t, nthreshold,
+                       thr_a, off_a, thr_b, off_b, z, weights, skipna, out):
+    from oracle import wb2_oracle as orc  # pylint: disable=import-outside-toplevel
+    self.calls.append(('gaussian_metrics', int(off_mean.size), nthreshold))
+    W = self._weights(weights)
+    nfield = off_mean.size
+    nt = max(nthreshold, 1)
+    res = np.zeros((nfield, nt, weights.nregion, 8))
+    for i in range(nfield):
+      f = _slab(mean, off_mean[i], weights, np.float32)
+      sd = _slab(std, off_std[i], weights, np.float32)
+      ts = _slab(t, off_t[i], weights, np.float32)
+      if nthreshold == 0:
+        point = [{0: orc.gaussian_crps_pointwise(f, sd, ts), 1: sd * sd}]
+      else:
+        thrs = self._threshold_fields(nthreshold, thr_a, off_a, thr_b, off_b,
+                                      z, i, nfield, weights)
+        point = [{0: orc.gaussian_brier_pointwise(f, sd, ts, thr),
+                  2: orc.gaussian_ignorance_pointwise(f, sd, ts, thr),
+                  3: orc.gaussian_rps_part_pointwise(f, sd, ts, thr)}
+                 for thr in thrs]
+      for k, stats in enumerate(point):
+        for r in range(weights.nregion):
+          for q, v in stats.items():
+            res[i, k, r, q], res[i, k, r, 4 + q] = self._wsum(
+                W[r], v, skipna, weights.zero_skip)
+    _view(out, res.size, np.float64)[...] = res.reshape(-1)
 
   def __getattr__(self, name):
     raise AttributeError(

@@ -222,3 +222,25 @@ def test_central_reliability_of_a_calibrated_histogram(n_bins):
   with pytest.raises(ValueError, match='Too few bins'):
     metrics.central_reliability(xl.Dataset(
         {'temperature': (('bins',), np.ones(2) / 2)}, {'bins': np.arange(2)}))
+
+
+def test_land_mask_device_copies_are_cached_per_context():
+  """The cached LandRegion mask is a DEVICE pointer: a second context (another
+  device, or a context created after the first was closed) must upload its
+  own copy, never reuse the first one's pointer."""
+  import fake_ctx
+  from weatherbench2_b200 import _spatial as sp, regions as R
+  lat = np.linspace(-90, 90, 7)
+  lon = np.linspace(0, 360, 12, endpoint=False)
+  lsm = (np.random.RandomState(0).rand(7, 12) > 0.5).astype(float)
+  shared = {}  # what metrics.py passes to ask for caching
+  a, b = fake_ctx.FakeContext(), fake_ctx.FakeContext()
+  ptrs = []
+  for ctx in (a, b, a):
+    (_, spec), = sp.build_weights(ctx, lat, lon, [R.LandRegion(lsm)],
+                                  'lat_lon', 12, shared)
+    assert spec.cell_w_dev in ctx._bufs  # owned by THIS context
+    ptrs.append(spec.cell_w_dev)
+  assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]  # one upload per context
+  assert a.h2d_bytes == b.h2d_bytes == lsm.size * 4
+  assert not shared  # the caller's dict is only a request flag

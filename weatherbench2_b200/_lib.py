@@ -298,6 +298,12 @@ class Context:
           except Exception:  # pylint: disable=broad-except
             pass
       self._pinned_pool.clear()
+      # device copies of LandRegion masks (_spatial.build_weights)
+      for ptr in self.__dict__.pop('_cell_weight_cache', {}).values():
+        try:
+          self.lib.wb2_free(self.handle, _P(ptr))
+        except Exception:  # pylint: disable=broad-except
+          pass
       self._closed = True
       self.lib.wb2_destroy(self.handle)
 

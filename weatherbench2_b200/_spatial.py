@@ -276,6 +276,10 @@ def build_weights(ctx: _lib.Context, latitude: np.ndarray,
   """
   wlat = lat_weights(latitude)
   facs = region_factors(regions, latitude, longitude)
+  if cell_cache is not None:
+    # the cached values are DEVICE pointers: they belong to this context (its
+    # device, its lifetime), whatever dict the caller passed to ask for caching
+    cell_cache = ctx.__dict__.setdefault('_cell_weight_cache', {})
   groups: dict = {}
   for i, fc in enumerate(facs):
     key = None if fc.cell is None else fc.cell.tobytes()
@@ -292,7 +296,7 @@ def build_weights(ctx: _lib.Context, latitude: np.ndarray,
       if key is not None:
         cell = facs[ids[0]].cell
         cell = cell if layout == 'lat_lon' else cell.T
-        cache_key = (key, layout)
+        cache_key = (key, cell.shape, layout)
         if cell_cache is not None and cache_key in cell_cache:
           cell_dev = cell_cache[cache_key]
         else:
