@@ -380,6 +380,194 @@ class FakeContext:
                 W[r], v, skipna, weights.zero_skip)
     _view(out, res.size, np.float64)[...] = res.reshape(-1)
 
+  # -- K9: SEEPS maps --------------------------------------------------------------
+  def seeps_maps(self, f, t, wet, p1, nout, ngroup, off_f, off_t, off_wet_f,
+                 off_wet_t, nrow, ncol, row_stride, wet_row_stride,
+                 dry_threshold, min_p1, max_p1, skipna, out):
+    from oracle import wb2_oracle as orc  # pylint: disable=import-outside-toplevel
+    self.calls.append(('seeps_maps', int(nout), int(ngroup)))
+    g = self._geometry(nrow, ncol, row_stride)
+    gw = self._geometry(nrow, ncol, wet_row_stride)
+    p1a = _view(p1, nrow * ncol, np.float32).reshape(nrow, ncol).astype(
+        np.float64)
+    res = np.empty((nout, nrow, ncol), dtype=np.float32)
+    for j in range(nout):
+      terms = []
+      for q in range(ngroup):
+        i = j * ngroup + q
+        with _quiet():
+          terms.append(orc.seeps_pointwise(
+              _slab(f, off_f[i], g, np.float32),
+              _slab(t, off_t[i], g, np.float32),
+              _slab(wet, off_wet_f[i], gw, np.float32),
+              _slab(wet, off_wet_t[i], gw, np.float32), p1a,
+              float(dry_threshold) * 1000.0, float(min_p1), float(max_p1)))
+      with _quiet():
+        res[j] = (np.nanmean if skipna else np.mean)(np.stack(terms), axis=0)
+    _view(out, res.size, np.float32)[...] = res.reshape(-1)
+
+  # -- K10: rank histogram ------------------------------------------------------------
+  def rank_histogram(self, x, t, nmember, member_stride, nout, ngroup, off_x,
+                     off_t, nrow, ncol, row_stride, nbins, random_ties, seed,
+                     out):
+    self.calls.append(('rank_histogram', int(nout), int(ngroup), int(nbins)))
+    g = self._geometry(nrow, ncol, row_stride)
+    rs = np.random.RandomState(int(seed) % (2**32))
+    width = (nmember + 1) // nbins
+    res = np.zeros((nout, nrow, ncol, nbins), dtype=np.float32)
+    for j in range(nout):
+      for q in range(ngroup):
+        i = j * ngroup + q
+        xs = np.stack([_slab(x + m * member_stride * 4, off_x[i], g, np.float32)
+                       for m in range(nmember)])
+        ts = _slab(t, off_t[i], g, np.float32)
+        with np.errstate(invalid='ignore'):
+          # NaN sorts last: members that are NaN never precede the truth
+          below = (xs < ts[None]).sum(axis=0)
+          if np.isnan(ts).any():
+            below = np.where(np.isnan(ts), (~np.isnan(xs)).sum(axis=0), below)
+          equal = (xs == ts[None]).sum(axis=0)
+        if random_ties:  # truth placed uniformly among the members equal to it
+          below = below + (rs.rand(*below.shape) * (equal + 1)).astype(int)
+        bins = below // width
+        res[j] += np.eye(nbins, dtype=np.float32)[bins] / ngroup
+    _view(out, res.size, np.float32)[...] = res.reshape(-1)
+
+  # -- K5 / K8: regridding -----------------------------------------------------------
+  @staticmethod
+  def _dense(csr: _lib.CsrSpec) -> np.ndarray:
+    w = np.zeros((csr.n_tgt, csr.n_src))
+    for i in range(csr.n_tgt):
+      lo, hi = csr.row_ptr[i], csr.row_ptr[i + 1]
+      w[i, csr.col_idx[lo:hi]] = csr.val[lo:hi]
+      if csr.nan_row[i]:
+        w[i] = np.nan
+    return w
+
+  def regrid_conservative(self, src, dst, nfield, src_stride, dst_stride, lon_w,
+                          lat_w):
+    self.calls.append(('regrid_conservative', int(nfield)))
+    wlon, wlat = self._dense(lon_w), self._dense(lat_w)
+    ns = lon_w.n_src * lat_w.n_src
+    nt = lon_w.n_tgt * lat_w.n_tgt
+    for i in range(nfield):
+      x = _view(src + i * src_stride * 4, ns, np.float32).reshape(
+          lon_w.n_src, lat_w.n_src).astype(np.float64)
+      ok = ~np.isnan(x)
+      with np.errstate(invalid='ignore', divide='ignore'):
+        num = np.einsum('ab,cd,bd->ac', wlon, wlat, np.where(ok, x, 0.0))
+        den = np.einsum('ab,cd,bd->ac', wlon, wlat, ok.astype(np.float64))
+        res = num / den
+      _view(dst + i * dst_stride * 4, nt, np.float32)[...] = res.astype(
+          np.float32).reshape(-1)
+
+  def regrid_conservative_host(self, *args):
+    self.regrid_conservative(*args)
+
+  def regrid_gather(self, src, dst, nfield, src_stride, dst_stride, nsource,
+                    indices):
+    self.calls.append(('regrid_gather', int(nfield)))
+    idx = np.asarray(indices)
+    if idx.size and (idx.min() < 0 or idx.max() >= nsource):
+      raise _lib.Wb2Error('wb2_regrid_gather: index out of range')
+    for i in range(nfield):
+      x = _view(src + i * src_stride * 4, nsource, np.float32)
+      _view(dst + i * dst_stride * 4, idx.size, np.float32)[...] = x[idx]
+
+  def regrid_bilinear(self, src, dst, nfield, src_stride, dst_stride,
+                      source_shape, lon_taps, lat_taps):
+    self.calls.append(('regrid_bilinear', int(nfield)))
+    nlon_s, nlat_s = source_shape
+
+    def lerp(a, i0, i1, frac, axis):
+      i0, i1 = np.asarray(i0), np.asarray(i1)
+      lo = np.take(a, np.maximum(i0, 0), axis=axis)
+      hi = np.take(a, np.maximum(i1, 0), axis=axis)
+      shape = [1, 1]
+      shape[axis] = -1
+      fr = np.asarray(frac, dtype=np.float32).reshape(shape)
+      val = lo + fr * (hi - lo)
+      outside = ((i0 < 0) | (i1 < 0)).reshape(shape)
+      return np.where(outside, np.float32(np.nan), val).astype(np.float32)
+
+    for i in range(nfield):
+      x = _view(src + i * src_stride * 4, nlon_s * nlat_s, np.float32).reshape(
+          nlon_s, nlat_s)
+      y = lerp(x, *lat_taps, axis=1)   # latitude first, then longitude
+      y = lerp(y, *lon_taps, axis=0)
+      _view(dst + i * dst_stride * 4, y.size, np.float32)[...] = y.reshape(-1)
+
+  # -- K4: zonal spectrum -------------------------------------------------------------
+  @staticmethod
+  def _spectra(x, nfield, nrow, ncol, scale):
+    a = _view(x, nfield * nrow * ncol, np.float32).reshape(nfield, nrow, ncol)
+    fk = np.fft.rfft(a.astype(np.float64), axis=-1, norm='forward')
+    s = np.abs(fk) ** 2
+    s[..., 1:] *= 2
+    return s * np.asarray(scale, dtype=np.float64)[None, :, None]
+
+  def zonal_spectrum(self, x, nfield, nrow, ncol, scale, out, accumulate=False,
+                     nfield_out=0):
+    self.calls.append(('zonal_spectrum', int(nfield), bool(accumulate)))
+    s = self._spectra(x, nfield, nrow, ncol, scale)
+    nk = ncol // 2 + 1
+    if not accumulate:
+      _view(out, s.size, np.float32)[...] = s.astype(np.float32).reshape(-1)
+      return
+    acc = _view(out, nfield_out * nrow * nk, np.float32).reshape(
+        nfield_out, nrow, nk)
+    for i in range(nfield):  # ADDED to slot i % nfield_out
+      acc[i % nfield_out] += s[i].astype(np.float32)
+
+  def zonal_spectrum_host(self, x, nfield, nrow, ncol, scale, out,
+                          accumulate=False, nfield_out=0):
+    if accumulate:  # the host entry OVERWRITES with the sum
+      nk = ncol // 2 + 1
+      _view(out, nfield_out * nrow * nk, np.float32)[...] = 0
+    self.zonal_spectrum(x, nfield, nrow, ncol, scale, out, accumulate,
+                        nfield_out)
+
+  def zonal_spectrum_latsum(self, x, nfield, nrow, ncol, scale, out,
+                            nfield_out):
+    self.calls.append(('zonal_spectrum_latsum', int(nfield), int(nfield_out)))
+    s = self._spectra(x, nfield, nrow, ncol, scale).sum(axis=1)
+    res = np.zeros((nfield_out, ncol // 2 + 1))
+    for i in range(nfield):
+      res[i % nfield_out] += s[i]
+    _view(out, res.size, np.float32)[...] = res.astype(np.float32).reshape(-1)
+
+  def zonal_spectrum_latsum_host(self, *args):
+    self.zonal_spectrum_latsum(*args)
+
+  # -- derived variables / preprocessing ------------------------------------------------
+  def wind_speed(self, u, v, out, n):
+    self.calls.append(('wind_speed', int(n)))
+    a, b = _view(u, n, np.float32), _view(v, n, np.float32)
+    _view(out, n, np.float32)[...] = np.sqrt(a * a + b * b)
+
+  def ens_mean(self, x, nmember, member_stride, off_x, slab, skipna, out):
+    self.calls.append(('ens_mean', int(np.size(off_x)), int(nmember)))
+    off_x = np.asarray(off_x)
+    res = _view(out, off_x.size * slab, np.float32).reshape(off_x.size, slab)
+    for i, off in enumerate(off_x):
+      xs = np.stack([_view(x + (int(off) + m * member_stride) * 4, slab,
+                           np.float32) for m in range(nmember)])
+      with _quiet():
+        res[i] = (np.nanmean if skipna else np.mean)(
+            xs.astype(np.float64), axis=0).astype(np.float32)
+
+  def spectrum_interp(self, spec, nfield, nrow, nk, freq_table, freqs, out):
+    self.calls.append(('spectrum_interp', int(nfield)))
+    a = _view(spec, nfield * nrow * nk, np.float32).reshape(nfield, nrow, nk)
+    table = np.asarray(freq_table, dtype=np.float64).reshape(nrow, nk)
+    fr = np.asarray(freqs, dtype=np.float64)
+    res = _view(out, nfield * nrow * fr.size, np.float32).reshape(
+        nfield, nrow, fr.size)
+    for i in range(nfield):
+      for r in range(nrow):
+        res[i, r] = np.interp(fr, table[r], a[i, r].astype(np.float64),
+                              left=np.nan, right=np.nan)
+
   def __getattr__(self, name):
     raise AttributeError(
         f'FakeContext has no emulation of {name!r}: this code path needs the '

@@ -88,3 +88,37 @@ test_probabilistic_and_spatial_configs = _on_stand_in(
     evp.test_probabilistic_and_spatial_configs)
 test_metric_and_region_loop_many_metrics_regions = _on_stand_in(
     ev.test_metric_and_region_loop_many_metrics_regions)
+
+# regridders (K5 / K8), zonal spectrum (K4 + latitude mean + interpolation),
+# derived variables / preprocessing, SEEPS (K9), rank histogram (K10)
+import test_derived_wind_gpu as wind  # noqa: E402  pylint: disable=wrong-import-position
+import test_preprocessing_gpu as prep  # noqa: E402  pylint: disable=wrong-import-position
+import test_rank_hist_gpu as rh  # noqa: E402  pylint: disable=wrong-import-position
+import test_regrid_interp_gpu as rgi  # noqa: E402  pylint: disable=wrong-import-position
+import test_regrid_spectrum_gpu as rgs  # noqa: E402  pylint: disable=wrong-import-position
+import test_seeps_gpu as seeps  # noqa: E402  pylint: disable=wrong-import-position
+
+for _mod, _names in (
+    (rgs, ('test_regridding_extrapolation_known_answer',
+           'test_expected_nans_and_oracle', 'test_regridding_nans_disc',
+           'test_regrid_dataset_flips_latitude_and_keeps_dims',
+           'test_spectrum_matches_oracle',
+           'test_spectrum_longitude_first_layout_and_peak',
+           'test_spectrum_parseval_and_time_sum')),
+    (rgi, ('test_bilinear_longitude_periodicity_known_answers',
+           'test_bilinear_latitude_poles_known_answers',
+           'test_nearest_exact_known_answer',
+           'test_regridders_match_oracle_on_random_fields')),
+    (wind, ('test_wind_speed_is_bit_identical_to_numpy',
+            'test_wind_speed_as_eval_derived_variable')),
+    (prep, ('test_ensemble_mean_matches_numpy_mean',
+            'test_interpolate_spectral_frequencies_matches_scipy_interp1d',
+            'test_latitude_mean_spectrum_operator')),
+    (seeps, ('test_seeps_known_answers',
+             'test_seeps_random_fields_match_oracle')),
+    (rh, ('test_rank_one_hot_matches_oracle_without_ties',
+          'test_repeated_entries_get_random_bin',
+          'test_partial_ties_stay_within_the_tied_bins',
+          'test_bad_num_bins_raises'))):
+  for _name in _names:
+    globals()[_name] = _on_stand_in(getattr(_mod, _name))

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import wb2_oracle as orc
+import wb2_testdata as td
 
 pytestmark = pytest.mark.gpu
 
@@ -14,7 +15,6 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize('shape', [(10, 3, 2, 19, 36), (50, 1, 33, 64),
                                    (7, 5, 9, 11)])
 def test_ensemble_mean_matches_numpy_mean(skipna, shape):
-  import torch
   from weatherbench2_b200 import preprocessing as pp, xarray_lite as xl
   rs = np.random.RandomState(sum(shape))
   x = (280 + 5 * rs.standard_normal(shape)).astype(np.float32)
@@ -24,7 +24,7 @@ def test_ensemble_mean_matches_numpy_mean(skipna, shape):
       ('time', 'level', 'latitude', 'longitude')[-(len(shape) - 1):])
   coords = {d: np.arange(n) for d, n in zip(dims, shape)}
   want = orc.ensemble_mean(x, 0, skipna)
-  for data in (x, torch.from_numpy(x).cuda()):
+  for data in td.host_and_device(x):
     ds = xl.Dataset({'t': (dims, data), 'orog': (dims[-2:], x[0, ..., :, :].reshape(
         (-1,) + shape[-2:])[0])}, coords)
     out = pp.compute_ensemble_mean(ds, skipna=skipna)
@@ -93,7 +93,6 @@ def test_latitude_mean_spectrum_operator(nlon, nlat):
   """ZonalEnergySpectrum.compute_latitude_mean == the weighted latitude mean
   of ZonalEnergySpectrum.compute (both vs the oracle), NumPy and CUDA inputs,
   with a time mean and a latitude band."""
-  import torch
   from weatherbench2_b200 import derived_variables as dvs, xarray_lite as xl
   rs = np.random.RandomState(nlat)
   lat = np.linspace(-90, 90, nlat)
@@ -103,7 +102,7 @@ def test_latitude_mean_spectrum_operator(nlon, nlat):
   coords = {'time': np.arange(4), 'level': np.array([200, 500, 850]),
             'latitude': lat, 'longitude': lon}
   op = dvs.ZonalEnergySpectrum('u')
-  for data in (x, torch.from_numpy(x).cuda()):
+  for data in td.host_and_device(x):
     ds = xl.Dataset({'u': (dims, data)}, coords)
     got = op.compute_latitude_mean(ds)
     want, wd = orc.zonal_energy_spectrum_latitude_mean(x, dims, lat, lon)

@@ -90,3 +90,13 @@ def get_random_truth_and_forecast(variables=('geopotential',),
       mock_forecast_data(ensemble_size=ensemble_size, lead_start=lead_start,
                          lead_stop=lead_stop, **kw), seed=seed + 1)
   return truth, forecast
+
+
+def host_and_device(x):
+  """The array as the operators may receive it: NumPy, and -- when a GPU is
+  present -- a CUDA tensor (the stand-in context of fake_ctx.py has no device
+  memory: it sees the NumPy case only)."""
+  yield x
+  import torch
+  if torch.cuda.is_available():
+    yield torch.from_numpy(x).cuda()
