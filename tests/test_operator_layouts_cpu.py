@@ -1,0 +1,128 @@
+"""Randomised differential tests of the operator layer's HOST logic against the
+oracle, on the NumPy stand-in context (tests/fake_ctx.py): dimension orders no
+dataset convention guarantees (spatial dims anywhere, truth with fewer or
+differently ordered dims than the forecast, the ensemble axis in the middle),
+float32 / float64, strided views, NaNs with and without skipna, regions.
+xarray arithmetic does not care about memory layout; the offset tables, layout
+decisions and broadcast rules of `_spatial.py` must not either."""
+import numpy as np
+import pytest
+
+import fake_ctx
+from oracle import wb2_oracle as orc
+
+REGIONS = [
+    lambda R: (None, None),
+    lambda R: (R.SliceRegion(lat_slice=slice(-40, 60)),
+               orc.SliceRegion(lat_slice=slice(-40, 60))),
+    lambda R: (R.ExtraTropicalRegion(), orc.ExtraTropicalRegion()),
+]
+
+
+def _case(rs, outer, forecast_only=()):
+  from weatherbench2_b200 import regions as R, xarray_lite as xl
+  nlat, nlon = int(rs.choice([5, 7, 12])), int(rs.choice([6, 8, 16]))
+  lat = np.linspace(-90, 90, nlat)
+  lon = np.linspace(0, 360, nlon, endpoint=False)
+  fnames = list(forecast_only) + [d for d in outer if d not in forecast_only
+                                  and rs.rand() < 0.8]
+  tnames = [d for d in fnames if d not in forecast_only and rs.rand() < 0.7]
+  fdims = fnames + ['latitude', 'longitude']
+  tdims = tnames + ['latitude', 'longitude']
+  rs.shuffle(fdims)
+  rs.shuffle(tdims)
+  size = dict(outer, latitude=nlat, longitude=nlon)
+  dtype = rs.choice([np.float32, np.float64]) if not forecast_only else (
+      np.float32)
+  f = rs.normal(size=[size[d] for d in fdims]).astype(dtype)
+  t = rs.normal(size=[size[d] for d in tdims]).astype(dtype)
+  if rs.rand() < 0.3:
+    f[rs.rand(*f.shape) < 0.05] = np.nan
+  fv = f
+  if rs.rand() < 0.3:  # every second element of a larger array
+    big = np.zeros([2 * s for s in f.shape], dtype=dtype)
+    view = tuple(slice(0, 2 * s, 2) for s in f.shape)
+    big[view] = f
+    fv = big[view]
+  coords = {'latitude': lat, 'longitude': lon}
+  coords.update({d: np.arange(n) for d, n in outer.items()})
+  fds = xl.Dataset({'z': (tuple(fdims), fv)},
+                   {k: v for k, v in coords.items() if k in fdims})
+  tds = xl.Dataset({'z': (tuple(tdims), t)},
+                   {k: v for k, v in coords.items() if k in tdims})
+  preg, oreg = REGIONS[rs.randint(len(REGIONS))](R)
+  return (fds, tds, f, tuple(fdims), t, tuple(tdims), lat, lon, preg, oreg,
+          bool(rs.rand() < 0.5))
+
+
+def _same(got, want, wd, atol):
+  assert set(got.dims) == set(wd), (got.dims, wd)
+  np.testing.assert_allclose(got.transpose(*wd).values, want, rtol=1e-5,
+                             atol=atol, equal_nan=True)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_deterministic_metrics_any_dimension_order(seed):
+  from weatherbench2_b200 import metrics
+  rs = np.random.RandomState(seed)
+  for _ in range(25):
+    outer = {'time': rs.randint(1, 4), 'level': rs.randint(1, 3),
+             'lead_time': rs.randint(1, 3)}
+    fds, tds, f, fd, t, td, lat, lon, preg, oreg, skipna = _case(rs, outer)
+    with fake_ctx.installed():
+      mse = metrics.MSE().compute_chunk(fds, tds, region=preg,
+                                        skipna=skipna)['z']
+      bias = metrics.Bias().compute_chunk(fds, tds, region=preg,
+                                          skipna=skipna)['z']
+    want, wd = orc.mse(f, fd, t, td, lat, lon, region=oreg, skipna=skipna)
+    _same(mse, want, wd, 1e-7)
+    want, wd = orc.bias(f, fd, t, td, lat, lon, region=oreg, skipna=skipna)
+    _same(bias, want, wd, 1e-6)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_ensemble_metrics_any_dimension_order(seed):
+  from weatherbench2_b200 import metrics
+  rs = np.random.RandomState(100 + seed)
+  for _ in range(20):
+    outer = {'time': rs.randint(1, 4), 'level': rs.randint(1, 3),
+             'realization': int(rs.choice([1, 2, 3, 5, 10]))}
+    fds, tds, f, fd, t, td, lat, lon, preg, oreg, skipna = _case(
+        rs, outer, forecast_only=('realization',))
+    with fake_ctx.installed():
+      crps = metrics.CRPS().compute_chunk(fds, tds, region=preg,
+                                          skipna=skipna)['z']
+      var = metrics.EnsembleVariance().compute_chunk(fds, tds, region=preg,
+                                                     skipna=skipna)['z']
+      maps = metrics.SpatialCRPS().compute_chunk(fds, tds, skipna=skipna)['z']
+    want, wd = orc.crps(f, fd, t, td, 'realization', lat, lon, region=oreg,
+                        skipna=skipna)
+    _same(crps, want, wd, 1e-6)
+    want, wd = orc.ensemble_variance(f, fd, 'realization', lat, lon,
+                                     region=oreg, skipna=skipna)
+    _same(var, want, wd, 1e-6)
+    want, wd = orc.spatial_ens_maps(f, fd, t, td, 'realization',
+                                    skipna)['crps']
+    _same(maps, want, wd, 1e-6)
+
+
+def test_interleaved_dimensions_are_compacted_not_rejected():
+  """(time, latitude, level, longitude): another dimension sits INSIDE the
+  (row, col) slab.  Forecast and truth with such dims in different orders used
+  to be refused ('must share ... row stride'); now each is packed into whole
+  slabs, and a plain strided box view stays zero-copy."""
+  from weatherbench2_b200 import _spatial as sp, xarray_lite as xl
+  a = np.arange(2 * 5 * 3 * 8, dtype=np.float32).reshape(2, 5, 3, 8)
+  op = sp.prepare_operand(xl.DataArray(
+      a, ('time', 'latitude', 'level', 'longitude')))
+  assert (op.layout, op.nrow, op.ncol, op.row_stride) == ('lat_lon', 5, 8, 8)
+  assert not np.shares_memory(op.data, a)
+  assert op.outer_dims == ('time', 'level')
+  box = np.zeros((2, 3, 5, 16), np.float32)[..., 4:12]  # longitude box
+  op = sp.prepare_operand(xl.DataArray(
+      box, ('time', 'level', 'latitude', 'longitude')))
+  assert op.row_stride == 16 and np.shares_memory(op.data, box)
+  bc = np.broadcast_to(a[0, :, 0][None], (4, 5, 8))  # stride-0 outer dim
+  op = sp.prepare_operand(xl.DataArray(bc, ('lead_time', 'latitude',
+                                            'longitude')))
+  assert op.outer_strides == (0,) and np.shares_memory(op.data, a)

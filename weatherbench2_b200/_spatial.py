@@ -112,14 +112,26 @@ def prepare_operand(da: xl.DataArray, want_layout: Optional[str] = None,
   ilat, ilon = dims.index(LAT), dims.index(LON)
   shape = tuple(data.shape)
 
+  def slab_is_whole(irow, icol):
+    # no other dimension may be interleaved with the (row, col) slab: every
+    # outer stride spans a whole slab (or is 0: a broadcast view).  Otherwise
+    # the slab of one field is scattered through memory -- two operands with
+    # the same dims in a different order would disagree on the row stride, and
+    # the kernels would stride through HBM -- so such arrays are compacted.
+    span = (shape[irow] - 1) * strides[irow] + shape[icol]
+    return all(shape[i] == 1 or strides[i] == 0 or strides[i] >= span
+               for i in range(len(shape)) if i not in (irow, icol))
+
   def layout_ok():
     if strides[ilon] == 1 or shape[ilon] == 1:
       lay = 'lat_lon'
-      if strides[ilat] >= shape[ilon] or shape[ilat] == 1:
+      if (strides[ilat] >= shape[ilon] or shape[ilat] == 1) and slab_is_whole(
+          ilat, ilon):
         return lay
     if strides[ilat] == 1 or shape[ilat] == 1:
       lay = 'lon_lat'
-      if strides[ilon] >= shape[ilat] or shape[ilon] == 1:
+      if (strides[ilon] >= shape[ilat] or shape[ilon] == 1) and slab_is_whole(
+          ilon, ilat):
         return lay
     return None
 
