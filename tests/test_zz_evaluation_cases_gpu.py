@@ -10,6 +10,7 @@ import contextlib
 import pytest
 
 import test_evaluation_cpu as cases
+import test_statistical_cases as stat
 
 pytestmark = pytest.mark.gpu
 
@@ -17,3 +18,13 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize('case', cases.CASES, ids=lambda c: c.__name__[5:])
 def test_in_memory_evaluation_on_device(case, tmp_path):
   case(tmp_path, contextlib.nullcontext, crps_rtol=5e-5, det_rtol=5e-6)
+
+
+def test_gaussian_crps_converges_on_device():
+  stat.case_gaussian_crps_converges(contextlib.nullcontext, exact_rtol=1e-4)
+
+
+@pytest.mark.parametrize('ensemble_size,num_bins', stat.RANK_HIST_CASES)
+def test_rank_histogram_calibration_on_device(ensemble_size, num_bins):
+  stat.case_rank_histogram_calibration(contextlib.nullcontext, ensemble_size,
+                                       num_bins)
