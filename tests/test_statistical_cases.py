@@ -112,3 +112,81 @@ def test_gaussian_crps_converges():
 @pytest.mark.parametrize('ensemble_size,num_bins', RANK_HIST_CASES)
 def test_rank_histogram_calibration(ensemble_size, num_bins):
   case_rank_histogram_calibration(fake_ctx.installed, ensemble_size, num_bins)
+
+
+# ------------------------------------------------------------------------------
+# regridding_test.py:72-249 (test_coarse_grid_interpolates): a smooth periodic
+# field regridded to half the resolution stays between the min and max of the
+# 2 x 2 source cells nearest to each target node -- for all three regridders,
+# both longitude schemes (incl. negative longitudes), with / without pole
+# nodes and custom latitudes.  Checks orientation and index alignment.
+# ------------------------------------------------------------------------------
+S0, C0 = 'START_AT_ZERO', 'CENTER_AT_ZERO'
+WP, NP_, CU = ('EQUIANGULAR_WITH_POLES', 'EQUIANGULAR_WITHOUT_POLES', 'CUSTOM')
+COARSE_GRID_CASES = [
+    # regridder, source lat spacing, source lon scheme, target lat, target lon
+    ('ConservativeRegridder', WP, C0, WP, C0),
+    ('ConservativeRegridder', WP, S0, WP, S0),
+    ('ConservativeRegridder', NP_, S0, NP_, S0),
+    ('ConservativeRegridder', WP, S0, WP, C0),
+    ('ConservativeRegridder', WP, C0, WP, S0),
+    ('ConservativeRegridder', NP_, C0, WP, S0),
+    ('BilinearRegridder', WP, S0, WP, C0),
+    ('BilinearRegridder', WP, C0, WP, S0),
+    ('ConservativeRegridder', WP, S0, WP, C0),
+    ('NearestRegridder', NP_, C0, WP, S0),
+    ('ConservativeRegridder', CU, S0, CU, S0),
+    ('ConservativeRegridder', NP_, S0, CU, S0),
+]
+
+
+def case_coarse_grid_interpolates(scope, regridder, source_lat, source_lon,
+                                  target_lat, target_lon):
+  from weatherbench2_b200 import regridding as rg, xarray_lite as xl
+  n_lats, n_lons, reduce_factor = 32, 64, 2
+
+  def lats(spacing, n):
+    if spacing == CU:
+      return np.linspace(-87.5, 87.5, n)
+    return rg.latitude_values(rg.LatitudeSpacing[spacing], n)
+
+  lat_s = lats(source_lat, n_lats)
+  lon_s = rg.longitude_values(rg.LongitudeScheme[source_lon], n_lons)
+  theta = 2 * np.pi * lon_s / 360
+  phi = 2 * np.pi * (lat_s - 90) / 180
+  x = np.sin(phi)[:, None] * (np.cos(theta) ** 2 + np.sin(theta))[None, :]
+  lat_t = lats(target_lat, n_lats // reduce_factor)
+  lon_t = rg.longitude_values(rg.LongitudeScheme[target_lon],
+                              n_lons // reduce_factor)
+  # source cells grouped under the target node they are nearest to
+  rolled = x if source_lon == target_lon else np.roll(x, n_lons // 2, axis=1)
+  blocks = rolled.reshape(n_lats // 2, 2, n_lons // 2, 2)
+  lower, upper = blocks.min(axis=(1, 3)), blocks.max(axis=(1, 3))
+  source = xl.Dataset(
+      {'X': (('time', 'latitude', 'longitude'), x[None])},
+      dict(time=np.array(['2000-01-01T00'], dtype='datetime64[ns]'),
+           latitude=lat_s, longitude=lon_s))
+  grid = lambda lo, la: rg.Grid(longitudes=lo, latitudes=la,  # noqa: E731
+                                includes_poles=True, periodic=True)
+  with scope():
+    out = getattr(rg, regridder)(grid(lon_s, lat_s), grid(lon_t, lat_t)
+                                 ).regrid_dataset(source)['X']
+  assert out.dims == ('time', 'latitude', 'longitude')
+  got = np.asarray(out.values)[0]
+  assert got.shape == lower.shape and np.isfinite(got).all()
+  np.testing.assert_array_equal(out.coords['longitude'].values, lon_t)
+  np.testing.assert_array_equal(out.coords['latitude'].values, lat_t)
+  if target_lat == CU:
+    min_frac = 0.97
+  elif source_lon == target_lon:
+    min_frac = 0.99
+  else:
+    min_frac = 0.5
+  assert (lower <= got).mean() >= min_frac
+  assert (got <= upper).mean() >= min_frac
+
+
+@pytest.mark.parametrize('case', COARSE_GRID_CASES,
+                         ids=lambda c: '-'.join(c))
+def test_coarse_grid_interpolates(case):
+  case_coarse_grid_interpolates(fake_ctx.installed, *case)

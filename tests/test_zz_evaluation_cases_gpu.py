@@ -28,3 +28,9 @@ def test_gaussian_crps_converges_on_device():
 def test_rank_histogram_calibration_on_device(ensemble_size, num_bins):
   stat.case_rank_histogram_calibration(contextlib.nullcontext, ensemble_size,
                                        num_bins)
+
+
+@pytest.mark.parametrize('case', stat.COARSE_GRID_CASES,
+                         ids=lambda c: '-'.join(c))
+def test_coarse_grid_interpolates_on_device(case):
+  stat.case_coarse_grid_interpolates(contextlib.nullcontext, *case)
