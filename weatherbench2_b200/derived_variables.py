@@ -289,3 +289,16 @@ def interpolate_spectral_frequencies(spectrum, wavenumber_dim: str,
 
 # Wind variables live in _derived_wind.py (they need DerivedVariable).
 from weatherbench2_b200._derived_wind import WindSpeed  # noqa: E402  pylint: disable=wrong-import-position
+
+# The named derived variables of weatherbench2/derived_variables.py:724-773 that
+# have a device implementation.  The remaining entries of the reference's table
+# (divergence / vorticity, geostrophic winds, lapse rate, column integrals,
+# relative humidity, precipitation accumulations) are data preparation off the
+# hot path and are not reproduced; asking for one raises KeyError here instead
+# of silently running on the host.
+DERIVED_VARIABLE_DICT = {
+    'wind_speed': WindSpeed(u_name='u_component_of_wind',
+                            v_name='v_component_of_wind'),
+    '10m_wind_speed': WindSpeed(u_name='10m_u_component_of_wind',
+                                v_name='10m_v_component_of_wind'),
+}
