@@ -10,6 +10,7 @@ import contextlib
 import pytest
 
 import test_evaluation_cpu as cases
+import test_official_configs as official
 import test_statistical_cases as stat
 
 pytestmark = pytest.mark.gpu
@@ -34,3 +35,11 @@ def test_rank_histogram_calibration_on_device(ensemble_size, num_bins):
                          ids=lambda c: '-'.join(c))
 def test_coarse_grid_interpolates_on_device(case):
   stat.case_coarse_grid_interpolates(contextlib.nullcontext, *case)
+
+
+def test_official_deterministic_configs_on_device(tmp_path):
+  official.case_official_deterministic_configs(tmp_path, contextlib.nullcontext)
+
+
+def test_official_probabilistic_configs_on_device(tmp_path):
+  official.case_official_probabilistic_configs(tmp_path, contextlib.nullcontext)
