@@ -58,3 +58,79 @@ def test_product_never_imports_the_oracle():
       if fn.endswith(('.py', '.cu', '.cuh', '.h')):
         src = open(os.path.join(dirpath, fn)).read()
         assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def _declarations():
+  """{name: (return type, [parameter types])} parsed from the header, types
+  normalised to a small vocabulary."""
+  text = open(os.path.join(ROOT, 'include', 'wb2b200.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  text = re.sub(r'//[^\n]*', '', text)
+  out = {}
+  for ret, name, params in re.findall(
+      r'\n\s*([A-Za-z_][\w\s\*]*?)\s*\b(wb2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;',
+      text):
+    plist = []
+    params = ' '.join(params.split())
+    if params not in ('', 'void'):
+      for p in params.split(','):
+        p = p.strip()
+        if '*' in p:
+          base = p[:p.rindex('*') + 1]
+        else:
+          base = ' '.join(p.split()[:-1])  # drop the parameter name
+        plist.append(' '.join(base.replace('*', ' * ').split()))
+    out[name] = (' '.join(ret.replace('*', ' * ').split()), plist)
+  return out
+
+
+def _ctype_class(c_type: str):
+  """The ctypes type a C parameter type must be bound as."""
+  import ctypes as C
+  from weatherbench2_b200 import _lib
+  t = c_type.replace('const ', '').strip()
+  scalars = {'int': C.c_int, 'int32_t': C.c_int32, 'int64_t': C.c_int64,
+             'uint64_t': C.c_uint64, 'size_t': C.c_size_t, 'float': C.c_float,
+             'double': C.c_double}
+  if t in scalars:
+    return [scalars[t]]
+  if t.endswith('* *'):                      # out-parameters: void** / ctx**
+    return [C.POINTER(C.c_void_p)]
+  if t == 'char *':
+    return [C.c_char_p]
+  if t in ('wb2_weights *',):
+    return [C.POINTER(_lib.Weights)]
+  if t in ('wb2_csr *',):
+    return [C.POINTER(_lib.Csr)]
+  typed = {'int64_t *': C.POINTER(C.c_int64), 'int32_t *': C.POINTER(C.c_int32),
+           'double *': C.POINTER(C.c_double), 'float *': C.POINTER(C.c_float)}
+  # data buffers are passed as raw addresses (c_void_p); descriptor arrays may
+  # be bound as typed pointers
+  if t in typed:
+    return [C.c_void_p, typed[t]]
+  if t.endswith('*'):
+    return [C.c_void_p]
+  raise AssertionError(f'unmapped C type {c_type!r}')
+
+
+def test_ctypes_prototypes_match_the_header_declarations():
+  """Every argument of every entry point: same count, and a ctypes type of the
+  right width / kind (an int32 bound as int64, or a missing parameter, would
+  corrupt the call silently)."""
+  import ctypes as C
+  from weatherbench2_b200 import _lib
+  decls = _declarations()
+  assert set(decls) == set(_lib.PROTOTYPES)
+  for name, (ret, params) in decls.items():
+    restype, argtypes = _lib.PROTOTYPES[name]
+    assert len(argtypes) == len(params), (name, params, argtypes)
+    for i, (c_type, bound) in enumerate(zip(params, argtypes)):
+      allowed = _ctype_class(c_type)
+      assert any(bound is a or (
+          C.sizeof(bound) == C.sizeof(a) and bound in (C.c_int, C.c_int32)
+          and a in (C.c_int, C.c_int32)) for a in allowed), (
+              name, i, c_type, bound)
+    want = {'int': C.c_int, 'int64_t': C.c_int64, 'const char *': C.c_char_p,
+            'void *': C.c_void_p}[ret]
+    assert restype is want or (restype in (C.c_int, C.c_int32) and
+                               want in (C.c_int, C.c_int32)), (name, ret)
