@@ -134,3 +134,30 @@ def test_ctypes_prototypes_match_the_header_declarations():
             'void *': C.c_void_p}[ret]
     assert restype is want or (restype in (C.c_int, C.c_int32) and
                                want in (C.c_int, C.c_int32)), (name, ret)
+
+
+def test_ctypes_structures_match_the_header_typedefs():
+  """wb2_weights / wb2_csr: same member names, order and scalar widths."""
+  import ctypes as C
+  from weatherbench2_b200 import _lib
+  text = open(os.path.join(ROOT, 'include', 'wb2b200.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  width = {'int32_t': 4, 'int64_t': 8, 'uint8_t': 1, 'float': 4, 'double': 8}
+  for cname, struct in (('wb2_weights', _lib.Weights), ('wb2_csr', _lib.Csr)):
+    body = re.search(r'typedef struct \{(.*?)\}\s*' + cname + ';', text,
+                     re.S).group(1)
+    members = []
+    for decl in body.split(';'):
+      decl = ' '.join(decl.split())
+      if decl:
+        name = re.search(r'(\w+)$', decl).group(1)
+        members.append((name, decl[:-len(name)].strip()))
+    assert [m[0] for m in members] == [f[0] for f in struct._fields_], cname
+    for (name, c_type), (_, bound) in zip(members, struct._fields_):
+      if '*' in c_type:
+        assert C.sizeof(bound) == C.sizeof(C.c_void_p), (cname, name)
+        target = c_type.replace('const', '').replace('*', '').strip()
+        if hasattr(bound, '_type_') and not isinstance(bound._type_, str):
+          assert C.sizeof(bound._type_) == width[target], (cname, name)
+      else:
+        assert C.sizeof(bound) == width[c_type], (cname, name)
