@@ -144,7 +144,7 @@ def test_ctypes_structures_match_the_header_typedefs():
   text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
   width = {'int32_t': 4, 'int64_t': 8, 'uint8_t': 1, 'float': 4, 'double': 8}
   for cname, struct in (('wb2_weights', _lib.Weights), ('wb2_csr', _lib.Csr)):
-    body = re.search(r'typedef struct \{(.*?)\}\s*' + cname + ';', text,
+    body = re.search(r'typedef struct \{([^{}]*)\}\s*' + cname + ';', text,
                      re.S).group(1)
     members = []
     for decl in body.split(';'):
