@@ -16,7 +16,7 @@ computes (results are tiny) is NumPy.
 from __future__ import annotations
 
 import numbers
-from typing import Any, Hashable, Iterable, Mapping, Optional, Sequence
+from typing import Any, Iterable, Mapping, Optional, Sequence
 
 import numpy as np
 
