@@ -264,3 +264,41 @@ def test_in_memory_and_distributed_consistency(tmp_path, by_init):
                                err_msg=name)
     # rank 0 wrote the file, as evaluate_in_memory does
     assert (tmp_path / 'beam' / f'{name}.npz').exists()
+
+
+def _idle_rank_worker(rank, world, port, temporal_mean, outdir):
+  import torch.distributed as dist
+  import fake_ctx
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  forecast, truth = _make_data(ninit=2)
+  with fake_ctx.installed() as fake:
+    res = wd.evaluate_sharded(forecast, truth, _eval_config(),
+                              temporal_mean=temporal_mean)
+  np.save(os.path.join(outdir, f'rank{rank}.npy'), res['z'].values)
+  np.save(os.path.join(outdir, f'calls{rank}.npy'), len(fake.calls))
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('temporal_mean', [True, False])
+def test_more_ranks_than_chunks(tmp_path, temporal_mean):
+  """Two init times over three ranks: the rank without a chunk still takes
+  part in the collective (zeros for the mean, nothing for the gather) and
+  every rank ends with the single-process result."""
+  import fake_ctx
+  world = 3
+  mp.spawn(_idle_rank_worker,
+           args=(world, _free_port(), temporal_mean, str(tmp_path)),
+           nprocs=world, join=True)
+  forecast, truth = _make_data(ninit=2)
+  with fake_ctx.installed():
+    want = wd.evaluate_sharded(forecast, truth, _eval_config(),
+                               temporal_mean=temporal_mean)['z'].values
+  for r in range(world):
+    np.testing.assert_allclose(np.load(tmp_path / f'rank{r}.npy'), want,
+                               rtol=1e-12)
+  calls = [int(np.load(tmp_path / f'calls{r}.npy')) for r in range(world)]
+  # chunks 0 and 1 go to ranks 0 and 1; for the mean the idle rank evaluates
+  # one probe chunk only to learn the payload shape
+  assert calls[:2] == [1, 1] and calls[2] == (1 if temporal_mean else 0)
