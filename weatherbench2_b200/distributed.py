@@ -30,6 +30,17 @@ def _dist():
   return dist
 
 
+def _nccl_device(device=None):
+  """The CUDA device this rank's collectives run on: the caller's choice, else
+  the device of the rank's wb2 context (LOCAL_RANK) -- NOT torch's current
+  device, which is cuda:0 on every rank unless the launcher set it."""
+  import torch  # pylint: disable=import-outside-toplevel
+  if device is not None:
+    return torch.device(device)
+  from weatherbench2_b200 import _lib  # pylint: disable=import-outside-toplevel
+  return torch.device('cuda', _lib.default_context().device)
+
+
 def all_reduce_sum(arrays: list, group=None, device=None) -> list:
   """Sum-all-reduce a list of float64 NumPy arrays in one collective.
   NCCL needs device tensors; gloo (CPU tests) takes host tensors."""
@@ -42,8 +53,7 @@ def all_reduce_sum(arrays: list, group=None, device=None) -> list:
   backend = dist.get_backend(group)
   tensor = torch.from_numpy(flat.copy())
   if backend == 'nccl':
-    tensor = tensor.to(device if device is not None else
-                       torch.device('cuda', torch.cuda.current_device()))
+    tensor = tensor.to(_nccl_device(device))
   dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
   flat = tensor.cpu().numpy()
   out, pos = [], 0
@@ -108,7 +118,7 @@ class TimeMeanAccumulator:
 
 
 def _gather_chunks(per_chunk: list, indices: list, chunk_dim: str, world: int,
-                   group=None) -> xl.Dataset:
+                   group=None, device=None) -> xl.Dataset:
   """All ranks' per-chunk results, concatenated along `chunk_dim` in chunk
   order (the un-reduced output of the reference's pipeline when
   `temporal_mean=False`).  Variables without `chunk_dim` (it was averaged or
@@ -120,7 +130,13 @@ def _gather_chunks(per_chunk: list, indices: list, chunk_dim: str, world: int,
                 {k: (c.dims, c.values) for k, c in ds.coords.items()})
                for i, ds in pairs]
     gathered = [None] * world
-    dist.all_gather_object(gathered, payload, group=group)
+    if dist.get_backend(group) == 'nccl':
+      import torch  # pylint: disable=import-outside-toplevel
+      # all_gather_object stages the pickles on torch's CURRENT device
+      with torch.cuda.device(_nccl_device(device)):
+        dist.all_gather_object(gathered, payload, group=group)
+    else:
+      dist.all_gather_object(gathered, payload, group=group)
     pairs = []
     for part in gathered:
       for i, data_vars, coords in part:
@@ -217,7 +233,7 @@ def evaluate_sharded(forecast: xl.Dataset, truth: xl.Dataset, eval_config,
       else:
         per_chunk.append(xl.from_xarray(res))
   if not temporal_mean:
-    return _gather_chunks(per_chunk, mine, chunk_dim, world, group)
+    return _gather_chunks(per_chunk, mine, chunk_dim, world, group, device)
   if not acc.sums:
     # a rank without chunks still has to take part in the collective with the
     # right payload shape: evaluate nothing, contribute zeros
