@@ -219,6 +219,29 @@ def test_probabilistic_climatology_stacks_years_as_members():
   assert da.values.dtype == np.float32
 
 
+def test_label_joins_compose_with_lazy_gathers():
+  """A by-valid persistence forecast covers fewer times than the truth: the
+  inner join of the metric arithmetic restricts the forecast's position table
+  instead of materialising the gathered forecast."""
+  from weatherbench2_b200 import evaluation, xarray_lite as xl
+  truth, tarr, ttimes, _ = _truth('2020-01-01', '2020-01-12', 6)
+  fc, _, vtimes, lead = _forecast('2020-01-02', '2020-01-06', 12, [0, 12, 24],
+                                  False)
+  fc = evaluation.apply_time_conventions(fc, by_init=False)
+  pf = evaluation.create_persistence_forecast(fc, truth)['geopotential']
+  a, b = xl.align_inner(pf, truth['geopotential'])
+  assert hasattr(a, 'lazy_source') and a._materialised is None  # pylint: disable=protected-access
+  assert pf._materialised is None  # pylint: disable=protected-access
+  np.testing.assert_array_equal(a.coords['time'].values,
+                                b.coords['time'].values)
+  kept, want = orc.persistence_like_forecast_by_valid(
+      tarr['geopotential'], ttimes, vtimes, lead)
+  np.testing.assert_array_equal(a.coords['time'].values, kept)
+  np.testing.assert_array_equal(a.values, want)
+  src, _ = a.lazy_source
+  assert np.shares_memory(src.values, tarr['geopotential'])
+
+
 def _rmse_time_mean(f, t, dims, lat, lon, avg):
   want, wd = orc.rmse_sqrt_before_time_avg(f, dims, t, dims, lat, lon)
   return want.mean(axis=wd.index(avg)), tuple(d for d in wd if d != avg)

@@ -1083,8 +1083,10 @@ def align_inner(a: DataArray, b: DataArray):
     return a, b
 
   def view(x, maps):
-    if hasattr(x, 'lazy_source'):  # nested gathers: materialise the inner one
-      x = DataArray(x.values, x.dims, x.coords, x.name, x.attrs)
+    if hasattr(x, 'lazy_source'):
+      # already a gathered view (a by-init truth, a climatological or
+      # persistence forecast): restrict its position tables, stay lazy
+      return x.isel({d: pos for d, (_, pos) in maps.items()})
     extra = {d: Coord((d,), x.coords[d].values[pos])
              for d, (_, pos) in maps.items()}
     return LazyGather(x, maps, extra_coords=extra)
