@@ -1045,7 +1045,12 @@ class LazyGather(DataArray):
           maps[sd] = (tdims, pos[tuple(sl)])
           looked_up = True
       if not looked_up:
-        source = source.isel({d: k})
+        if isinstance(k, slice):
+          source = source.isel({d: k})  # a view of the source
+        else:
+          # picking labels of an untouched dimension becomes one more lookup:
+          # nothing of the (possibly very long) source record is copied
+          maps[d] = ((d,), np.asarray(k, dtype=np.int64))
     key = [norm.get(d, slice(None)) for d in self.dims]
     coords = self._isel_coords(key, drop)
     out = LazyGather(source, maps)
