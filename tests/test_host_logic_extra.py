@@ -244,3 +244,18 @@ def test_land_mask_device_copies_are_cached_per_context():
   assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]  # one upload per context
   assert a.h2d_bytes == b.h2d_bytes == lsm.size * 4
   assert not shared  # the caller's dict is only a request flag
+
+
+def test_land_mask_with_missing_values_is_refused():
+  """xarray's `weighted()` raises on NaN weights (the mask is a factor of the
+  weights, regions.py:138 / metrics.py:161); with a threshold the comparison
+  turns NaN into 0 first (regions.py:136-137)."""
+  from weatherbench2_b200 import regions as R
+  lat = np.linspace(-90, 90, 5)
+  lon = np.linspace(0, 360, 8, endpoint=False)
+  lsm = np.ones((5, 8))
+  lsm[2, 3] = np.nan
+  with pytest.raises(ValueError, match='cannot contain missing values'):
+    R.LandRegion(lsm).factors(lat, lon)
+  cell = R.LandRegion(lsm, threshold=0.5).factors(lat, lon).cell
+  assert cell[2, 3] == 0 and cell.sum() == 39

@@ -134,6 +134,11 @@ class LandRegion(Region):
     m = m.astype(np.float64)
     if self.threshold is not None:
       m = (m > self.threshold).astype(np.float64)  # regions.py:136-137
+    elif np.isnan(m).any():
+      # the mask becomes part of the weights of `dataset.weighted(...)`
+      # (metrics.py:161), and xarray refuses weights with missing values
+      raise ValueError('`weights` cannot contain missing values. Missing '
+                       'values can be replaced by `weights.fillna(0)`.')
     return m
 
   def apply(self, dataset, weights):
