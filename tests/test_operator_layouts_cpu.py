@@ -126,3 +126,51 @@ def test_interleaved_dimensions_are_compacted_not_rejected():
   op = sp.prepare_operand(xl.DataArray(bc, ('lead_time', 'latitude',
                                             'longitude')))
   assert op.outer_strides == (0,) and np.shares_memory(op.data, a)
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_spectrum_and_regridder_any_dimension_order(seed):
+  """ZonalEnergySpectrum.compute moves the transformed dimension last
+  (apply_ufunc's core-dim rule, derived_variables.py:597-626) and
+  Regridder.regrid_dataset keeps the input's order (regridding.py:193-209),
+  wherever latitude / longitude sit."""
+  from weatherbench2_b200 import (derived_variables as dvs, regridding as rg,
+                                  xarray_lite as xl)
+  rs = np.random.RandomState(200 + seed)
+  for _ in range(12):
+    nlat, nlon = int(rs.choice([9, 13, 19])), int(rs.choice([16, 24, 36]))
+    lat = np.linspace(-90, 90, nlat)
+    lon = np.linspace(0, 360, nlon, endpoint=False)
+    dims = ['time', 'level', 'latitude', 'longitude']
+    rs.shuffle(dims)
+    dims = tuple(dims)
+    size = dict(time=rs.randint(1, 4), level=rs.randint(1, 3), latitude=nlat,
+                longitude=nlon)
+    x = rs.standard_normal([size[d] for d in dims]).astype(
+        rs.choice([np.float32, np.float64]))
+    ds = xl.Dataset({'u': (dims, x)}, dict(
+        time=np.arange(size['time']), level=np.arange(size['level']),
+        latitude=lat, longitude=lon))
+    x32 = x.astype(np.float32)
+    with fake_ctx.installed():
+      got = dvs.ZonalEnergySpectrum('u').compute(ds)
+    want, wd, _, _ = orc.zonal_energy_spectrum(x32, dims, lat, lon)
+    assert got.dims == wd
+    total = np.abs(want).sum(axis=-1, keepdims=True)
+    assert np.max(np.abs(got.values - want) / total) < 1e-5
+    target = rg.Grid.from_degrees(
+        np.linspace(0, 360, nlon // 2, endpoint=False),
+        np.linspace(-90, 90, (nlat + 1) // 2))
+    with fake_ctx.installed():
+      out = rg.ConservativeRegridder(rg.Grid.from_degrees(lon, lat),
+                                     target).regrid_dataset(ds)['u']
+    assert out.dims == dims
+    outer = [d for d in dims if d not in ('longitude', 'latitude')]
+    moved = np.moveaxis(x32, [dims.index('longitude'), dims.index('latitude')],
+                        [-2, -1])
+    want = orc.conservative_regrid(
+        moved, orc.Grid(lon, lat),
+        orc.Grid(np.asarray(target.longitudes), np.asarray(target.latitudes)))
+    np.testing.assert_allclose(
+        out.transpose(*outer, 'longitude', 'latitude').values, want, rtol=2e-5,
+        atol=2e-6)
