@@ -106,11 +106,12 @@ def test_ensemble_metrics_any_dimension_order(seed):
     _same(maps, want, wd, 1e-6)
 
 
-def test_interleaved_dimensions_are_compacted_not_rejected():
+def test_scattered_slabs_are_compacted_not_rejected():
   """(time, latitude, level, longitude): another dimension sits INSIDE the
-  (row, col) slab.  Forecast and truth with such dims in different orders used
-  to be refused ('must share ... row stride'); now each is packed into whole
-  slabs, and a plain strided box view stays zero-copy."""
+  (row, col) slab; a longitude box or every second row leaves gaps between
+  rows.  Forecast and truth that differed in such details used to be refused
+  ('must share ... row stride'); now every operand whose slab is not one dense
+  block is packed, and views made of whole dense slabs stay zero-copy."""
   from weatherbench2_b200 import _spatial as sp, xarray_lite as xl
   a = np.arange(2 * 5 * 3 * 8, dtype=np.float32).reshape(2, 5, 3, 8)
   op = sp.prepare_operand(xl.DataArray(
@@ -118,14 +119,20 @@ def test_interleaved_dimensions_are_compacted_not_rejected():
   assert (op.layout, op.nrow, op.ncol, op.row_stride) == ('lat_lon', 5, 8, 8)
   assert not np.shares_memory(op.data, a)
   assert op.outer_dims == ('time', 'level')
+  np.testing.assert_array_equal(op.data, np.moveaxis(a, 2, 1))
   box = np.zeros((2, 3, 5, 16), np.float32)[..., 4:12]  # longitude box
   op = sp.prepare_operand(xl.DataArray(
       box, ('time', 'level', 'latitude', 'longitude')))
-  assert op.row_stride == 16 and np.shares_memory(op.data, box)
-  bc = np.broadcast_to(a[0, :, 0][None], (4, 5, 8))  # stride-0 outer dim
+  assert op.row_stride == op.ncol == 8 and not np.shares_memory(op.data, box)
+  # whole dense slabs, strided / broadcast OUTER dimensions: nothing is copied
+  b = np.zeros((6, 3, 5, 8), np.float32)
+  op = sp.prepare_operand(xl.DataArray(
+      b[::2, 1:], ('time', 'level', 'latitude', 'longitude')))
+  assert np.shares_memory(op.data, b) and op.outer_strides == (240, 40)
+  bc = np.broadcast_to(b[0, 0][None], (4, 5, 8))  # stride-0 outer dim
   op = sp.prepare_operand(xl.DataArray(bc, ('lead_time', 'latitude',
                                             'longitude')))
-  assert op.outer_strides == (0,) and np.shares_memory(op.data, a)
+  assert op.outer_strides == (0,) and np.shares_memory(op.data, b)
 
 
 @pytest.mark.parametrize('seed', range(3))
@@ -174,3 +181,32 @@ def test_spectrum_and_regridder_any_dimension_order(seed):
     np.testing.assert_allclose(
         out.transpose(*outer, 'longitude', 'latitude').values, want, rtol=2e-5,
         atol=2e-6)
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_energy_score_rank_histogram_and_maps_any_dimension_order(seed):
+  """K3, K10 and K6 through their operators; the deterministic map is fed an
+  integer pick of the member axis (a strided view with gaps between rows)."""
+  from weatherbench2_b200 import metrics
+  rs = np.random.RandomState(300 + seed)
+  for _ in range(15):
+    outer = {'time': rs.randint(1, 4), 'level': rs.randint(1, 3),
+             'realization': int(rs.choice([2, 3, 5, 9]))}
+    fds, tds, f, fd, t, td, lat, lon, _, _, _ = _case(
+        rs, outer, forecast_only=('realization',))
+    f = np.nan_to_num(f)  # K3 has no skipna path of its own
+    fds = type(fds)({'z': (fd, f)}, fds.coords)
+    with fake_ctx.installed():
+      es = metrics.EnergyScore().compute_chunk(fds, tds)['z']
+      rh = metrics.RankHistogram().compute_chunk(fds, tds)['z']
+      sm = metrics.SpatialMSE().compute_chunk(fds.isel(realization=0),
+                                              tds)['z']
+    want, wd = orc.energy_score(f, fd, t, td, 'realization', lat, lon)
+    _same(es, want, wd, 1e-6)
+    want, wd = orc.rank_histogram_one_hot(f, fd, t, td, 'realization')
+    assert set(rh.dims) == set(wd)
+    np.testing.assert_array_equal(rh.transpose(*wd).values, want)
+    f0 = np.take(f, 0, axis=fd.index('realization'))
+    want, wd = orc.spatial_det_map(
+        'mse', f0, tuple(d for d in fd if d != 'realization'), t, td)
+    _same(sm, want, wd, 1e-7)

@@ -123,14 +123,19 @@ def prepare_operand(da: xl.DataArray, want_layout: Optional[str] = None,
                for i in range(len(shape)) if i not in (irow, icol))
 
   def layout_ok():
+    # rows must also be densely packed (row stride == ncol): operands of one
+    # launch share ONE row stride in the C ABI, and a strided view on one side
+    # (a longitude box, every second row, an integer pick of an inner
+    # dimension) against a dense array on the other would otherwise be
+    # refused.  Such views are compacted; whole-slab views stay zero-copy.
     if strides[ilon] == 1 or shape[ilon] == 1:
       lay = 'lat_lon'
-      if (strides[ilat] >= shape[ilon] or shape[ilat] == 1) and slab_is_whole(
+      if (strides[ilat] == shape[ilon] or shape[ilat] == 1) and slab_is_whole(
           ilat, ilon):
         return lay
     if strides[ilat] == 1 or shape[ilat] == 1:
       lay = 'lon_lat'
-      if (strides[ilon] >= shape[ilat] or shape[ilon] == 1) and slab_is_whole(
+      if (strides[ilon] == shape[ilat] or shape[ilon] == 1) and slab_is_whole(
           ilon, ilat):
         return lay
     return None
