@@ -210,3 +210,55 @@ def test_energy_score_rank_histogram_and_maps_any_dimension_order(seed):
     want, wd = orc.spatial_det_map(
         'mse', f0, tuple(d for d in fd if d != 'realization'), t, td)
     _same(sm, want, wd, 1e-7)
+
+
+@pytest.mark.parametrize('seed', range(2))
+def test_acc_climatology_lookup_any_dimension_order(seed):
+  """ACC (metrics.py:387-414): climatology with or without `hour`, with more
+  levels than the forecast, every array with its own dimension order; the
+  day-of-year / hour / level lookups are folded into the offset table."""
+  import pandas as pd
+  from weatherbench2_b200 import metrics, xarray_lite as xl
+  rs = np.random.RandomState(400 + seed)
+  hour12 = np.timedelta64(12, 'h')
+  for _ in range(15):
+    nlat, nlon = int(rs.choice([5, 7])), int(rs.choice([6, 8]))
+    lat = np.linspace(-90, 90, nlat)
+    lon = np.linspace(0, 360, nlon, endpoint=False)
+    ntime, nlev = rs.randint(1, 5), rs.randint(1, 3)
+    times = np.datetime64('2020-12-30T00', 'ns') + np.arange(ntime) * hour12
+    levels = np.array([500, 850])[:nlev]
+    clev = np.array([300, 500, 850]) if rs.rand() < 0.5 else levels
+    has_hour = rs.rand() < 0.5
+    base = ['time', 'level', 'latitude', 'longitude']
+    fdims, tdims = list(base), list(base)
+    cdims = (['hour'] if has_hour else []) + ['dayofyear'] + base[1:]
+    for dims in (fdims, tdims, cdims):
+      rs.shuffle(dims)
+    size = dict(time=ntime, level=nlev, latitude=nlat, longitude=nlon, hour=2,
+                dayofyear=366)
+    f = rs.normal(size=[size[d] for d in fdims]).astype(np.float32)
+    t = rs.normal(size=[size[d] for d in tdims]).astype(np.float32)
+    c = rs.normal(size=[dict(size, level=clev.size)[d] for d in cdims]).astype(
+        np.float32)
+    coords = dict(latitude=lat, longitude=lon, time=times, level=levels)
+    ccoords = dict(latitude=lat, longitude=lon, level=clev,
+                   dayofyear=np.arange(1, 367))
+    if has_hour:
+      ccoords['hour'] = np.array([0, 12])
+    skipna = bool(rs.rand() < 0.5)
+    with fake_ctx.installed():
+      got = metrics.ACC(climatology=xl.Dataset({'z': (tuple(cdims), c)},
+                                               ccoords)).compute_chunk(
+          xl.Dataset({'z': (tuple(fdims), f)}, coords),
+          xl.Dataset({'z': (tuple(tdims), t)}, coords), skipna=skipna)['z']
+    lead = (['hour'] if has_hour else []) + ['dayofyear'] + base[1:]
+    cc = np.transpose(c, [cdims.index(d) for d in lead])
+    pick = [list(clev).index(v) for v in levels]
+    rows = []
+    for stamp in pd.DatetimeIndex(times):
+      slab = cc[stamp.hour // 12] if has_hour else cc
+      rows.append(slab[stamp.dayofyear - 1][pick])
+    want, wd = orc.acc(f, tuple(fdims), t, tuple(tdims), np.stack(rows),
+                       tuple(base), lat, lon, skipna=skipna)
+    _same(got, want, wd, 1e-6)
