@@ -1,0 +1,301 @@
+"""Stand-in `xarray` used ONLY by tests/golden/make_reference_vectors.py to
+execute the reference's own metrics.py / regions.py / thresholds.py / utils.py
+in this container, where xarray itself cannot be installed (no network).
+
+It is `weatherbench2_b200.xarray_lite` plus the rest of the xarray API those
+four reference modules call (weighted means, the `.dt` accessor, apply_ufunc,
+dot, cumsum, quantile, ...), each written to xarray's documented semantics.
+The vectors it produces are therefore "the reference's code on a
+re-implemented xarray subset": they pin the oracle's restatement of the
+REFERENCE logic; xarray's own semantics remain restated (here and, separately,
+in oracle/wb2_oracle.py, which does not use this module).
+"""
+import numpy as np
+import pandas as pd
+
+from weatherbench2_b200 import xarray_lite as _xl
+from weatherbench2_b200.xarray_lite import (DataArray, Dataset, concat, merge,
+                                            zeros_like)
+
+__version__ = '0.0-shim'
+
+
+# ---- free functions ----------------------------------------------------------
+def where(cond, x, y):
+  """xr.where: element-wise choice with broadcasting by dimension name."""
+  base = next((o for o in (cond, x, y) if isinstance(o, (DataArray, Dataset))),
+              None)
+  if isinstance(base, Dataset) or any(isinstance(o, Dataset)
+                                      for o in (cond, x, y)):
+    ds = next(o for o in (cond, x, y) if isinstance(o, Dataset))
+    out = Dataset(attrs=None)
+    for k in ds.keys():
+      pick = lambda o: o[k] if isinstance(o, Dataset) else o  # noqa: E731
+      out[k] = where(pick(cond), pick(x), pick(y))
+    return out
+  cond = cond if isinstance(cond, DataArray) else DataArray(np.asarray(cond))
+  zero = cond * 0  # carries dims / coords
+  cx = (zero + x) if not isinstance(x, DataArray) else x
+  cy = (zero + y) if not isinstance(y, DataArray) else y
+  c, a = _xl._broadcast(cond, cx)[0:2], None  # pylint: disable=protected-access
+  del c, a
+  total = zero + cx * 0 + cy * 0  # the broadcast shape of all three
+  cb = (total + cond).values != 0 if cond.dtype != bool else (
+      (total + cond.astype(float)).values != 0)
+  xb = (total * 0 + cx).values if np.isfinite(total.values).all() else None
+  if xb is None:  # NaN / inf inside operands: broadcast without arithmetic
+    xb = _bcast(cx, total)
+    yb = _bcast(cy, total)
+    cb = _bcast(cond.astype(float), total) != 0
+  else:
+    yb = (total * 0 + cy).values
+  return DataArray(np.where(cb, xb, yb), total.dims, total.coords)
+
+
+def _bcast(da, like):
+  perm = [da.dims.index(d) for d in like.dims if d in da.dims]
+  v = np.transpose(da.values, perm)
+  v = v[tuple(slice(None) if d in da.dims else None for d in like.dims)]
+  return np.broadcast_to(v, like.shape)
+
+
+def apply_ufunc(func, *args, **kwargs):
+  """Only the element-wise form the reference uses: func(array) -> array."""
+  if kwargs:
+    raise NotImplementedError(f'apply_ufunc kwargs {sorted(kwargs)}')
+  first = args[0]
+  if isinstance(first, Dataset):
+    return first._map(lambda v: apply_ufunc(func, v, *args[1:]))  # pylint: disable=protected-access
+  raw = [a.values if isinstance(a, DataArray) else a for a in args]
+  return first._replace(np.asarray(func(*raw)))  # pylint: disable=protected-access
+
+
+def dot(a, b, dims=None, dim=None):
+  """xr.dot: sum of products over `dims` (NaN propagates)."""
+  dims = dims if dims is not None else dim
+  dims = (dims,) if isinstance(dims, str) else tuple(dims)
+  return (a * b).sum(dims, skipna=False)
+
+
+class _Weighted:
+  """DatasetWeighted / DataArrayWeighted .mean (xarray/core/weighted.py):
+  sum_of_weights uses the NOT-NULL mask of the data whatever `skipna`; the
+  weighted sum fills NaN with 0 only when skipna; 0 weight-sum -> NaN."""
+
+  def __init__(self, obj, weights):
+    if np.isnan(np.asarray(weights.values, dtype=float)).any():
+      raise ValueError('`weights` cannot contain missing values. Missing '
+                       'values can be replaced by `weights.fillna(0)`.')
+    self.obj, self.weights = obj, weights
+
+  def _mean_da(self, da, dim, skipna):
+    dim = tuple(d for d in dim if d in da.dims)
+    w = self.weights
+    if skipna or (skipna is None and da.dtype.kind in 'cfO'):
+      data = da.fillna(0.0)
+    else:
+      data = da
+    wsum = dot(data, w, dims=dim)
+    mask = da.notnull()
+    sow = dot(mask.astype(float) if hasattr(mask, 'astype') else mask, w,
+              dims=dim)
+    sow = sow.where(sow != 0.0)
+    return wsum / sow
+
+  def mean(self, dim=None, skipna=None, keep_attrs=None):
+    del keep_attrs
+    dim = (dim,) if isinstance(dim, str) else tuple(dim)
+    if isinstance(self.obj, Dataset):
+      return self.obj._map(lambda v: self._mean_da(v, dim, skipna))  # pylint: disable=protected-access
+    return self._mean_da(self.obj, dim, skipna)
+
+
+def _weighted(self, weights):
+  return _Weighted(self, weights)
+
+
+DataArray.weighted = _weighted
+Dataset.weighted = _weighted
+
+
+class _Dt:
+  def __init__(self, da):
+    self._da = da
+    self._idx = pd.DatetimeIndex(np.asarray(da.values).ravel())
+
+  def _field(self, name):
+    v = np.asarray(getattr(self._idx, name)).reshape(self._da.shape)
+    return self._da._replace(v)  # pylint: disable=protected-access
+
+  dayofyear = property(lambda self: self._field('dayofyear'))
+  hour = property(lambda self: self._field('hour'))
+  year = property(lambda self: self._field('year'))
+
+
+DataArray.dt = property(_Dt)
+
+for _cls in (DataArray, Dataset):
+  _cls.load = lambda self, **kw: self
+  _cls.compute = lambda self, **kw: self
+  _cls.chunk = lambda self, *a, **kw: self
+
+
+# ---- methods xarray_lite does not need for the product ------------------------
+def _ds_where(self, cond, other=np.nan):
+  pick = lambda o, k: o[k] if isinstance(o, Dataset) else o  # noqa: E731
+  out = Dataset(attrs=self.attrs)
+  for k in self.keys():
+    out[k] = self[k].where(pick(cond, k), pick(other, k))
+  return out
+
+
+def _da_where(self, cond, other=np.nan):
+  """DataArray.where with broadcasting by name (cond may have fewer dims)."""
+  if isinstance(cond, DataArray):
+    return where(cond, self, other)
+  return self._replace(np.where(np.asarray(cond), self.values, other))  # pylint: disable=protected-access
+
+
+DataArray.where = _da_where
+Dataset.where = _ds_where
+Dataset.fillna = lambda self, value: self._map(lambda v: v.fillna(value))  # pylint: disable=protected-access
+Dataset.isnull = lambda self: self._map(lambda v: v.isnull())  # pylint: disable=protected-access
+Dataset.notnull = lambda self: self._map(lambda v: v.notnull())  # pylint: disable=protected-access
+Dataset.astype = lambda self, dtype: self._map(lambda v: v.astype(dtype))  # pylint: disable=protected-access
+
+
+def _ds_map(self, func, keep_attrs=None, args=(), **kwargs):
+  del keep_attrs
+  out = Dataset(attrs=self.attrs)
+  for k in self.keys():
+    out[k] = func(self[k], *args, **kwargs)
+  return out
+
+
+Dataset.map = _ds_map
+
+
+def _moment(self, dim, skipna, ddof, root):
+  dims = (dim,) if isinstance(dim, str) else tuple(dim)
+  axes = tuple(self.dims.index(d) for d in dims)
+  v = np.asarray(self.values, dtype=np.float64 if self.dtype.kind != 'f'
+                 else self.dtype)
+  nan_aware = skipna or (skipna is None and v.dtype.kind == 'f')
+  import warnings
+  with warnings.catch_warnings(), np.errstate(invalid='ignore',
+                                              divide='ignore'):
+    warnings.simplefilter('ignore', RuntimeWarning)
+    r = (np.nanvar if nan_aware else np.var)(v, axis=axes, ddof=ddof)
+  if root:
+    r = np.sqrt(r)
+  keep = tuple(d for d in self.dims if d not in dims)
+  return self._replace(r, keep)  # pylint: disable=protected-access
+
+
+DataArray.var = lambda self, dim=None, skipna=None, ddof=0, **kw: _moment(
+    self, dim, skipna, ddof, False)
+DataArray.std = lambda self, dim=None, skipna=None, ddof=0, **kw: _moment(
+    self, dim, skipna, ddof, True)
+Dataset.var = lambda self, dim=None, skipna=None, ddof=0, **kw: self._map(  # pylint: disable=protected-access
+    lambda v: v.var(dim, skipna, ddof) if dim in v.dims else v)
+Dataset.std = lambda self, dim=None, skipna=None, ddof=0, **kw: self._map(  # pylint: disable=protected-access
+    lambda v: v.std(dim, skipna, ddof) if dim in v.dims else v)
+Dataset.min = lambda self, dim=None, skipna=None, **kw: self._map(  # pylint: disable=protected-access
+    lambda v: v.min(dim, skipna))
+Dataset.max = lambda self, dim=None, skipna=None, **kw: self._map(  # pylint: disable=protected-access
+    lambda v: v.max(dim, skipna))
+
+
+def _da_cumsum(self, dim, skipna=None):
+  del skipna
+  return self._replace(np.cumsum(self.values, axis=self.dims.index(dim)))  # pylint: disable=protected-access
+
+
+DataArray.cumsum = _da_cumsum
+Dataset.cumsum = lambda self, dim, skipna=None: self._map(  # pylint: disable=protected-access
+    lambda v: v.cumsum(dim) if dim in v.dims else v)
+
+
+def _da_argmin(self, dim):
+  ax = self.dims.index(dim)
+  keep = tuple(d for d in self.dims if d != dim)
+  return self._replace(np.argmin(self.values, axis=ax), keep)  # pylint: disable=protected-access
+
+
+DataArray.argmin = _da_argmin
+
+
+# ---- arithmetic aligns shared dimensions by label (join='inner') ----------------
+_plain_binary = DataArray._binary  # pylint: disable=protected-access
+
+
+def _align_inner(a, b):
+  """xarray's default arithmetic join: along every shared dimension that both
+  operands label, keep the labels present in both, in the order of `a`."""
+  for d in a.dims:
+    if d not in b.dims or d not in a.coords or d not in b.coords:
+      continue
+    ca, cb = a.coords[d].values, b.coords[d].values
+    if ca.shape == cb.shape and np.array_equal(ca, cb):
+      continue
+    keep = np.isin(ca, cb)
+    a = a.isel({d: np.nonzero(keep)[0]})
+    b = b.isel({d: _xl._lookup(cb, ca[keep])})  # pylint: disable=protected-access
+  return a, b
+
+
+def _aligned_binary(self, other, op, reflexive=False):
+  if isinstance(other, DataArray):
+    a, b = _align_inner(self, other)
+    return _plain_binary(a, b, op, reflexive)
+  return _plain_binary(self, other, op, reflexive)
+
+
+DataArray._binary = _aligned_binary  # pylint: disable=protected-access
+
+for _name, _op in (('__gt__', np.greater), ('__lt__', np.less),
+                   ('__ge__', np.greater_equal), ('__le__', np.less_equal)):
+  setattr(Dataset, _name,
+          lambda self, o, _op=_op: self._binary(o, _op))  # pylint: disable=protected-access
+
+
+# ---- .sel with several N-d indexers that share dimensions: pointwise -----------
+_plain_da_sel = DataArray.sel
+
+
+def _da_sel(self, indexers=None, method=None, drop=False, tolerance=None,
+            **kw):
+  idx = dict(indexers or {}, **kw)
+  vec = {d: v for d, v in idx.items()
+         if isinstance(v, DataArray) and d in self.dims and v.ndim >= 1 and
+         v.dims != (d,)}
+  rest = {d: v for d, v in idx.items() if d not in vec and d in self.dims}
+  out = self
+  if vec:
+    maps, extra = {}, {}
+    for d, lab in vec.items():
+      pos = _xl._lookup(out.coords[d].values, lab.values.ravel(), method)  # pylint: disable=protected-access
+      maps[d] = (lab.dims, pos.reshape(lab.shape))
+      for k, c in lab.coords.items():
+        extra.setdefault(k, c)
+      extra[d] = _xl.Coord(lab.dims, lab.values)
+    lazy = _xl.LazyGather(out, maps, extra_coords=extra)
+    out = DataArray(lazy.values, lazy.dims, lazy.coords, out.name, out.attrs)
+  if rest:
+    if tolerance is not None:
+      for d, v in rest.items():
+        have = out.coords[d].values
+        want = np.atleast_1d(np.asarray(v.values if isinstance(v, DataArray)
+                                        else v, dtype=float))
+        near = np.abs(have[None, :] - want[:, None]).min(axis=1)
+        if (near > tolerance).any():
+          raise KeyError(f'not all values found in index {d!r}')
+    out = _plain_da_sel(out, rest, method=method, drop=drop)
+  return out
+
+
+DataArray.sel = _da_sel
+Dataset.sel = lambda self, indexers=None, method=None, drop=False, \
+    tolerance=None, **kw: self._map(lambda v: v.sel(  # pylint: disable=protected-access
+        {d: k for d, k in dict(indexers or {}, **kw).items() if d in v.dims},
+        method=method, drop=drop, tolerance=tolerance))

@@ -1,0 +1,238 @@
+"""Vectors the REFERENCE's own metric classes produced in the build container
+(tests/golden/make_reference_vectors.py: weatherbench2/metrics.py, regions.py,
+thresholds.py executed on a re-implemented xarray subset, since xarray cannot
+be installed there) against
+
+  * the product operators on the NumPy stand-in context (same classes, same
+    arguments as the reference call that made the vector), and
+  * the oracle's restatement of the same call.
+
+169 calls: every deterministic / ensemble / energy-score / spatial / Gaussian /
+threshold metric, the region family, NaNs with and without skipna.  The CUDA
+kernels face the same vectors in tests/test_zz_evaluation_cases_gpu.py."""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pytest
+
+import fake_ctx
+from oracle import wb2_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+import reference_cases as rc  # noqa: E402  pylint: disable=wrong-import-position
+
+VECTORS = np.load(os.path.join(HERE, 'golden', 'reference_run_vectors.npz'))
+BY_CASE = {}
+for _key in VECTORS.files:
+  _cid, _var, _dims = _key.split('|')
+  BY_CASE.setdefault(_cid, {})[_var] = (
+      tuple(d for d in _dims.split(',') if d), VECTORS[_key])
+
+
+def product_lib():
+  from weatherbench2_b200 import metrics, regions, thresholds
+  return types.SimpleNamespace(metrics=metrics, regions=regions,
+                               thresholds=thresholds)
+
+
+def check_against_vectors(case, got, rtol=1e-5, atol=1e-6):
+  want = BY_CASE[case['id']]
+  assert set(got) == set(want), (sorted(got), sorted(want))
+  for var, (dims, ref) in want.items():
+    gd, gv = got[var]
+    assert set(gd) == set(dims), (case['id'], var, gd, dims)
+    gv = np.transpose(gv, [gd.index(d) for d in dims])
+    np.testing.assert_array_equal(np.isnan(gv), np.isnan(ref),
+                                  err_msg=f"{case['id']} {var}: NaN pattern")
+    np.testing.assert_allclose(gv, ref, rtol=rtol, atol=atol, equal_nan=True,
+                               err_msg=f"{case['id']} {var}")
+
+
+def run_product(case, scope):
+  from weatherbench2_b200 import xarray_lite as xl
+  arr = rc.arrays()
+  ds = rc.datasets(xl.Dataset, arr)
+  with scope(), warnings.catch_warnings():
+    warnings.simplefilter('ignore', RuntimeWarning)
+    return rc.run_case(product_lib(), case, ds, arr, xl.DataArray)
+
+
+def test_every_case_has_a_vector():
+  assert set(BY_CASE) == {c['id'] for c in rc.CASES}
+  assert len(rc.CASES) == 169
+
+
+@pytest.mark.parametrize('case', rc.CASES, ids=lambda c: c['id'])
+def test_product_operators_match_the_reference_run(case):
+  check_against_vectors(case, run_product(case, fake_ctx.installed))
+
+
+# ------------------------------------------------------------------------------
+# The oracle, restating each call on plain arrays
+# ------------------------------------------------------------------------------
+EDIMS = ('realization',) + rc.DIMS
+
+
+def _oracle_region(spec, arr):
+  if spec is None:
+    return None
+  kind = spec['type']
+  if kind == 'SliceRegion':
+    return orc.SliceRegion(lat_slice=rc._slices(spec.get('lat')),  # pylint: disable=protected-access
+                           lon_slice=rc._slices(spec.get('lon')))  # pylint: disable=protected-access
+  if kind == 'ExtraTropicalRegion':
+    return orc.ExtraTropicalRegion()
+  if kind == 'LandRegion':
+    return orc.LandRegion(arr[spec['mask']], threshold=spec.get('threshold'),
+                          latitude=rc.LAT, longitude=rc.LON)
+  return orc.CombinedRegion([_oracle_region(s, arr) for s in spec['regions']])
+
+
+def _clim_at_times(a, lead_axes=0):
+  """climatology (..., hour, dayofyear, level, lon, lat) -> (..., time, ...)."""
+  import pandas as pd
+  stamps = pd.DatetimeIndex(rc.TIMES)
+  hour = np.asarray(stamps.hour) // 12
+  doy = np.asarray(stamps.dayofyear) - 1
+  idx = (slice(None),) * lead_axes + (hour, doy)
+  return a[idx]
+
+
+def _thresholds(kind, arr):
+  """[(threshold array on (time, level, lon, lat))] per quantile."""
+  if kind == 'QuantileThreshold':
+    q = _clim_at_times(arr['clim/' + rc.Z + '_quantile'], lead_axes=1)
+    return [q[k] for k in range(rc.QUANTILES.size)]
+  mean = _clim_at_times(arr['clim/' + rc.Z])
+  std = _clim_at_times(arr['clim/' + rc.Z + '_std'])
+  return [orc.gaussian_quantile_threshold(mean, std, float(q))
+          for q in rc.QUANTILES]
+
+
+def run_oracle(case, arr):
+  metric, kw = case['metric'], case.get('kwargs', {})
+  region = _oracle_region(case.get('region'), arr)
+  skipna = case.get('skipna', False)
+  lat, lon = rc.LAT, rc.LON
+  f_key, t_key = case['forecast'], case['truth']
+  t_name = {'truth_z': 'truth'}.get(t_key, t_key)
+  f_name = {'det_z': 'det'}.get(f_key, f_key)
+  out = {}
+
+  def sa(values, dims):
+    return orc.spatial_average(values, dims, lat, lon, region, skipna)
+
+  def finish(var, values, dims):
+    if case.get('method') == 'compute':
+      values, dims = orc.time_mean(values, dims, skipna=skipna)
+    out[var] = (tuple(dims), values)
+
+  simple = {'MSE': orc.mse, 'MAE': orc.mae, 'Bias': orc.bias,
+            'RMSESqrtBeforeTimeAvg': orc.rmse_sqrt_before_time_avg}
+  if metric in simple:
+    variables = [v for v in (rc.Z, rc.U, rc.V) if f'{f_name}/{v}' in arr]
+    for v in variables:
+      r, d = simple[metric](arr[f'{f_name}/{v}'], rc.DIMS,
+                            arr[f'{t_name}/{v}'], rc.DIMS, lat, lon, region,
+                            skipna)
+      finish(v, r, d)
+    if 'wind_vector' in kw:
+      r, d = orc.wind_vector_mse(
+          arr[f'{f_name}/{rc.U}'], arr[f'{f_name}/{rc.V}'], rc.DIMS,
+          arr[f'{t_name}/{rc.U}'], arr[f'{t_name}/{rc.V}'], rc.DIMS, lat, lon,
+          region, skipna)
+      finish('wind_vector', np.sqrt(r) if metric != 'MSE' else r, d)
+    return out
+  f = arr[f'{f_name}/{rc.Z}']
+  t = arr[f'{t_name}/{rc.Z}']
+  if metric == 'ACC':
+    r, d = orc.acc(f, rc.DIMS, t, rc.DIMS, _clim_at_times(arr['clim/' + rc.Z]),
+                   rc.DIMS, lat, lon, region, skipna)
+    finish(rc.Z, r, d)
+  elif metric in ('SpatialMSE', 'SpatialMAE', 'SpatialBias'):
+    for v in (rc.Z, rc.U, rc.V):
+      if f'{f_name}/{v}' in arr:
+        r, d = orc.spatial_det_map(metric[7:].lower(), arr[f'{f_name}/{v}'],
+                                   rc.DIMS, arr[f'{t_name}/{v}'], rc.DIMS)
+        finish(v, r, d)
+  elif metric in ('CRPS', 'CRPSSkill', 'EnsembleMeanMSE',
+                  'EnsembleMeanRMSESqrtBeforeTimeAvg',
+                  'DebiasedEnsembleMeanMSE', 'EnergyScore',
+                  'EnergyScoreSkill'):
+    fn = {'CRPS': orc.crps, 'CRPSSkill': orc.crps_skill,
+          'EnsembleMeanMSE': orc.ensemble_mean_mse,
+          'EnsembleMeanRMSESqrtBeforeTimeAvg':
+              orc.ensemble_mean_rmse_sqrt_before_time_avg,
+          'DebiasedEnsembleMeanMSE': orc.debiased_ensemble_mean_mse,
+          'EnergyScore': orc.energy_score,
+          'EnergyScoreSkill': orc.energy_score_skill}[metric]
+    r, d = fn(f, EDIMS, t, rc.DIMS, 'realization', lat, lon, region=region,
+              skipna=skipna)
+    finish(rc.Z, r, d)
+  elif metric in ('CRPSSpread', 'EnsembleVariance',
+                  'EnsembleStddevSqrtBeforeTimeAvg', 'EnergyScoreSpread'):
+    fn = {'CRPSSpread': orc.crps_spread,
+          'EnsembleVariance': orc.ensemble_variance,
+          'EnsembleStddevSqrtBeforeTimeAvg':
+              orc.ensemble_stddev_sqrt_before_time_avg,
+          'EnergyScoreSpread': orc.energy_score_spread}[metric]
+    r, d = fn(f, EDIMS, 'realization', lat, lon, region=region, skipna=skipna)
+    finish(rc.Z, r, d)
+  elif metric in ('SpatialCRPS', 'SpatialCRPSSkill', 'SpatialCRPSSpread',
+                  'SpatialEnsembleVariance', 'SpatialEnsembleMeanMSE',
+                  'DebiasedSpatialEnsembleMeanMSE'):
+    key = {'SpatialCRPS': 'crps', 'SpatialCRPSSkill': 'skill',
+           'SpatialCRPSSpread': 'spread', 'SpatialEnsembleVariance': 'variance',
+           'SpatialEnsembleMeanMSE': 'mse',
+           'DebiasedSpatialEnsembleMeanMSE': 'debiased'}[metric]
+    r, d = orc.spatial_ens_maps(f, EDIMS, t, rc.DIMS, 'realization',
+                                skipna)[key]
+    finish(rc.Z, r, d)
+  elif metric in ('GaussianCRPS', 'GaussianVariance'):
+    s = arr['gauss/' + rc.Z + '_std']
+    point = (orc.gaussian_crps_pointwise(f, s, t) if metric == 'GaussianCRPS'
+             else s.astype(np.float64) ** 2)
+    finish(rc.Z, *sa(point, rc.DIMS))
+  elif metric.startswith('Gaussian'):
+    s = arr['gauss/' + rc.Z + '_std']
+    fn = {'GaussianBrierScore': orc.gaussian_brier_pointwise,
+          'GaussianIgnoranceScore': orc.gaussian_ignorance_pointwise,
+          'GaussianRPS': orc.gaussian_rps_part_pointwise}[metric]
+    parts = [sa(fn(f, s, t, thr), rc.DIMS)
+             for thr in _thresholds(kw['thresholds'], arr)]
+    _stack_thresholds(metric, parts, finish)
+  else:  # ensemble threshold metrics, spatially averaged or maps
+    spatial = metric.startswith('Spatial')
+    name = metric.replace('Spatial', '')
+    parts = []
+    for thr in _thresholds(kw['thresholds'], arr):
+      if 'Brier' in name:
+        p = orc.ens_brier_pointwise(f, t, thr, 0, 'Debiased' in name, skipna)
+      elif 'Ignorance' in name:
+        p = orc.ens_ignorance_pointwise(f, t, thr, 0, skipna)
+      else:
+        p = orc.ens_rps_part_pointwise(f, t, thr, 0, skipna)
+      parts.append((p, rc.DIMS) if spatial else sa(p, rc.DIMS))
+    _stack_thresholds(name, parts, finish)
+  return out
+
+
+def _stack_thresholds(name, parts, finish):
+  if name.endswith('RPS'):  # `.sum('quantile')`: xarray skips NaN by default
+    finish(rc.Z, np.nansum(np.stack([p for p, _ in parts]), axis=0),
+           parts[0][1])
+  else:
+    finish(rc.Z, np.stack([p for p, _ in parts]),
+           ('quantile',) + tuple(parts[0][1]))
+
+
+@pytest.mark.parametrize('case', rc.CASES, ids=lambda c: c['id'])
+def test_oracle_matches_the_reference_run(case):
+  with warnings.catch_warnings():
+    warnings.simplefilter('ignore', RuntimeWarning)
+    got = run_oracle(case, rc.arrays())
+  check_against_vectors(case, got, rtol=2e-6, atol=1e-7)

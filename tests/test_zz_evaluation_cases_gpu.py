@@ -43,3 +43,15 @@ def test_official_deterministic_configs_on_device(tmp_path):
 
 def test_official_probabilistic_configs_on_device(tmp_path):
   official.case_official_probabilistic_configs(tmp_path, contextlib.nullcontext)
+
+
+import test_reference_run_vectors as refrun  # noqa: E402  pylint: disable=wrong-import-position
+
+
+@pytest.mark.parametrize('case', refrun.rc.CASES, ids=lambda c: c['id'])
+def test_cuda_operators_match_the_reference_run(case):
+  """The vectors the reference's own metrics.py produced (tests/golden/
+  make_reference_vectors.py) against the CUDA kernels."""
+  refrun.check_against_vectors(
+      case, refrun.run_product(case, contextlib.nullcontext), rtol=2e-5,
+      atol=2e-6)
