@@ -27,9 +27,46 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(HERE, 'xarray_shim'), '/root/reference', HERE]
 
 import xarray as xr  # noqa: E402  (the shim)
-from weatherbench2 import metrics, regions, thresholds  # noqa: E402
+from weatherbench2 import config, evaluation, metrics, regions, thresholds  # noqa: E402
 
 import reference_cases as rc  # noqa: E402
+import reference_eval_cases as rec  # noqa: E402
+
+
+def run_evaluations(out) -> list:
+  """weatherbench2.evaluation.evaluate_in_memory on the eval cases; datasets
+  travel through the shim's in-memory "zarr" registry, results come back from
+  the files the reference wrote."""
+  import pickle
+  import tempfile
+  lib = types.SimpleNamespace(config=config, metrics=metrics, regions=regions,
+                              Dataset=xr.Dataset)
+
+  def source(name, dataset):
+    xr.register_store(f'mem://{name}', dataset)
+    return f'mem://{name}'
+
+  failed = []
+  with tempfile.TemporaryDirectory() as tmp:
+    for case, data_config, eval_configs in rec.build(lib, source, tmp):
+      for eval_name, eval_config in eval_configs.items():
+        key = f'eval:{case}/{eval_name}'
+        try:
+          with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            evaluation.evaluate_in_memory(data_config,
+                                          {eval_name: eval_config})
+          with open(os.path.join(tmp, f'{eval_name}.nc'), 'rb') as f:
+            res = pickle.load(f)
+        except Exception:  # pylint: disable=broad-except
+          failed.append(key)
+          print('FAILED', key)
+          traceback.print_exc(limit=-4)
+          continue
+        for var, (dims, values) in res['vars'].items():
+          out[f"{key}|{var}|{','.join(dims)}"] = values
+        print('ran', key, {v: d for v, (d, _) in res['vars'].items()})
+  return failed
 
 
 def main():
@@ -51,6 +88,7 @@ def main():
     for var, (dims, values) in res.items():
       out[f"{case['id']}|{var}|{','.join(dims)}"] = values
   print(f'{len(rc.CASES) - len(failed)} / {len(rc.CASES)} cases ran')
+  failed += run_evaluations(out)
   if failed:
     sys.exit(1)
   np.savez_compressed(os.path.join(HERE, 'reference_run_vectors.npz'), **out)

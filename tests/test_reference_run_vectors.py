@@ -236,3 +236,52 @@ def test_oracle_matches_the_reference_run(case):
     warnings.simplefilter('ignore', RuntimeWarning)
     got = run_oracle(case, rc.arrays())
   check_against_vectors(case, got, rtol=2e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------
+# evaluate_in_memory: the result files the reference's own evaluation.py wrote
+# ------------------------------------------------------------------------------
+import reference_eval_cases as rec  # noqa: E402  pylint: disable=wrong-import-position
+
+EVAL_VECTORS = {}
+for _key in VECTORS.files:
+  if _key.startswith('eval:'):
+    _cid, _var, _dims = _key.split('|')
+    EVAL_VECTORS.setdefault(_cid[5:], {})[_var] = (tuple(_dims.split(',')),
+                                                   VECTORS[_key])
+
+
+def check_product_evaluations(scope, tmp_path, rtol=1e-5, atol=1e-6):
+  from weatherbench2_b200 import (config, evaluation, metrics, regions,
+                                  xarray_lite as xl)
+  lib = types.SimpleNamespace(config=config, metrics=metrics, regions=regions,
+                              Dataset=xl.Dataset)
+  seen = set()
+  for case, data_config, eval_configs in rec.build(
+      lib, lambda name, dataset: dataset, str(tmp_path)):
+    with scope(), warnings.catch_warnings():
+      warnings.simplefilter('ignore', RuntimeWarning)
+      out = evaluation.evaluate_in_memory(data_config, eval_configs)
+    for eval_name, res in out.items():
+      key = f'{case}/{eval_name}'
+      seen.add(key)
+      want = EVAL_VECTORS[key]
+      assert set(res.keys()) == set(want), key
+      for var, (dims, ref) in want.items():
+        da = res[var]
+        assert set(da.dims) == set(dims), (key, da.dims, dims)
+        got = np.asarray(da.transpose(*dims).values, dtype=np.float64)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref),
+                                      err_msg=key)
+        np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol,
+                                   equal_nan=True, err_msg=key)
+  assert seen == set(EVAL_VECTORS) and len(seen) == 11
+
+
+def test_evaluate_in_memory_matches_the_reference_run(tmp_path):
+  """All eval configs of reference_eval_cases.py: plain / by region /
+  temporal_mean=False / climatological, probabilistic-climatological and
+  persistence forecasts / analysis as truth (by-init and by-valid) / latitude,
+  longitude, level and time selection / pressure-level suffixes / by-valid step
+  thinning -- product on the stand-in context vs the reference's result files."""
+  check_product_evaluations(fake_ctx.installed, tmp_path)

@@ -55,3 +55,8 @@ def test_cuda_operators_match_the_reference_run(case):
   refrun.check_against_vectors(
       case, refrun.run_product(case, contextlib.nullcontext), rtol=2e-5,
       atol=2e-6)
+
+
+def test_evaluate_in_memory_matches_the_reference_run_on_device(tmp_path):
+  refrun.check_product_evaluations(contextlib.nullcontext, tmp_path, rtol=2e-5,
+                                   atol=2e-6)
