@@ -28,6 +28,8 @@ import reference_cases as rc  # noqa: E402  pylint: disable=wrong-import-positio
 VECTORS = np.load(os.path.join(HERE, 'golden', 'reference_run_vectors.npz'))
 BY_CASE = {}
 for _key in VECTORS.files:
+  if _key.startswith('eval:'):  # evaluate_in_memory result files, see below
+    continue
   _cid, _var, _dims = _key.split('|')
   BY_CASE.setdefault(_cid, {})[_var] = (
       tuple(d for d in _dims.split(',') if d), VECTORS[_key])
