@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(HERE, 'xarray_shim'), '/root/reference', HERE]
 
 import xarray as xr  # noqa: E402  (the shim)
-from weatherbench2 import config, evaluation, metrics, regions, thresholds  # noqa: E402
+from weatherbench2 import (config, derived_variables, evaluation, metrics,  # noqa: E402
+                           regions, thresholds)
 
 import reference_cases as rc  # noqa: E402
 import reference_eval_cases as rec  # noqa: E402
@@ -89,6 +90,19 @@ def main():
       out[f"{case['id']}|{var}|{','.join(dims)}"] = values
   print(f'{len(rc.CASES) - len(failed)} / {len(rc.CASES)} cases ran')
   failed += run_evaluations(out)
+  try:
+    with warnings.catch_warnings():
+      warnings.simplefilter('ignore', RuntimeWarning)
+      extras = rc.run_extras(
+          types.SimpleNamespace(metrics=metrics,
+                                derived_variables=derived_variables),
+          xr.Dataset, arr)
+    for name, (dims, values) in extras.items():
+      out[f"extra:{name}||{','.join(dims)}"] = values
+    print('ran', len(extras), 'extra calls')
+  except Exception:  # pylint: disable=broad-except
+    failed.append('extras')
+    traceback.print_exc(limit=-6)
   if failed:
     sys.exit(1)
   np.savez_compressed(os.path.join(HERE, 'reference_run_vectors.npz'), **out)

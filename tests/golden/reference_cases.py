@@ -229,3 +229,86 @@ def _cases():
 
 
 CASES = _cases()
+
+
+# ------------------------------------------------------------------------------
+# Calls with other shapes: rank histogram + central reliability, SEEPS, zonal
+# energy spectrum + frequency interpolation, wind speed
+# ------------------------------------------------------------------------------
+PRECIP = 'total_precipitation_24hr'
+
+
+def extra_inputs():
+  rs = np.random.RandomState(424242)
+  h = np.timedelta64(1, 'h').astype('timedelta64[ns]')
+  init = TIMES[:3]
+  lead = np.array([0, 12]) * h
+  shape = (init.size, lead.size, NLON, NLAT)
+  wet = lambda: np.where(rs.uniform(size=shape) < 0.3, 0.0,  # noqa: E731
+                         rs.gamma(0.6, 0.002, size=shape)).astype(np.float32)
+  pf, pt = wet(), wet()
+  pf.flat[::17] = np.float32(0.00025)   # exactly AT the dry threshold
+  pf.flat[5::41] = np.nan
+  cshape = (2, 366, NLON, NLAT)
+  return dict(
+      init=init, lead=lead, pf=pf, pt=pt,
+      dry=rs.uniform(0.0, 1.0, cshape).astype(np.float32),
+      thr=rs.uniform(0.0005, 0.004, cshape).astype(np.float32),
+      field=(rs.standard_normal((3, 2, NLAT, 36)) + 0.3).astype(np.float32),
+      hist=np.array([0.2, 0.05, 0.1, 0.1, 0.25, 0.3]))
+
+
+def run_extras(lib, Dataset, arr):  # pylint: disable=invalid-name
+  """{name: (dims, values)}; `lib` has metrics and derived_variables."""
+  x = extra_inputs()
+  ds = datasets(Dataset, arr)
+  out = {}
+
+  def put(name, da):
+    out[name] = (tuple(da.dims), np.asarray(da.values))
+
+  for bins in (None, 3):
+    r = lib.metrics.RankHistogram(
+        ensemble_dim='realization', num_bins=bins).compute_chunk(
+            ds['ens5'], ds['truth_z'])[Z]
+    put(f'rank_histogram/bins={bins}', r)
+  hist = Dataset({Z: (('bins',), x['hist'])}, {'bins': np.arange(6)})
+  rel = lib.metrics.central_reliability(hist)[Z]
+  put('central_reliability', rel)
+  put('central_reliability/desired_prob', rel['desired_prob'])
+  # SEEPS on a by-init forecast (needs the valid_time coordinate)
+  pdims = ('init_time', 'lead_time', 'longitude', 'latitude')
+  pcoords = dict(init_time=x['init'], lead_time=x['lead'], longitude=LON,
+                 latitude=LAT,
+                 valid_time=(('init_time', 'lead_time'),
+                             x['init'][:, None] + x['lead'][None, :]))
+  cdims = ('hour', 'dayofyear', 'longitude', 'latitude')
+  clim = Dataset({PRECIP + '_seeps_dry_fraction': (cdims, x['dry']),
+                  PRECIP + '_seeps_threshold': (cdims, x['thr'])},
+                 dict(hour=np.array([0, 12]), dayofyear=np.arange(1, 367),
+                      longitude=LON, latitude=LAT))
+  pfd = Dataset({PRECIP: (pdims, x['pf'])}, pcoords)
+  ptd = Dataset({PRECIP: (pdims, x['pt'])}, pcoords)
+  put('seeps', lib.metrics.SEEPS(climatology=clim).compute_chunk(
+      pfd, ptd)[PRECIP])
+  put('spatial_seeps', lib.metrics.SpatialSEEPS(
+      climatology=clim, min_p1=0.3, max_p1=0.7).compute_chunk(pfd, ptd)[PRECIP])
+  # zonal energy spectrum of a (time, level, latitude, longitude) field
+  lon36 = np.linspace(0, 360, 36, endpoint=False)
+  sds = Dataset({U: (('time', 'level', 'latitude', 'longitude'), x['field']),
+                 V: (('time', 'level', 'latitude', 'longitude'),
+                     x['field'][::-1].copy())},
+                dict(time=TIMES[:3], level=LEVELS, latitude=LAT,
+                     longitude=lon36))
+  spec = lib.derived_variables.ZonalEnergySpectrum(U).compute(sds)
+  put('spectrum', spec)
+  put('spectrum/frequency', spec['frequency'])
+  put('spectrum/wavelength', spec['wavelength'])
+  inner = spec.isel(latitude=slice(1, NLAT - 1))  # the poles have zero length
+  interp = lib.derived_variables.interpolate_spectral_frequencies(
+      inner, 'zonal_wavenumber')
+  put('spectrum_interp', interp)
+  put('spectrum_interp/frequency', interp['frequency'])
+  put('wind_speed', lib.derived_variables.WindSpeed(
+      u_name=U, v_name=V).compute(sds))
+  return out

@@ -461,3 +461,185 @@ DataArray.all = lambda self, dim=None, axis=None, **kw: bool(
 DataArray.any = lambda self, dim=None, axis=None, **kw: bool(
     np.any(self.values))
 DataArray.__bool__ = lambda self: bool(np.asarray(self.values))
+
+
+# ---- what derived_variables.py (zonal spectrum, interpolation) and
+# RankHistogram add ---------------------------------------------------------------
+_elementwise_apply_ufunc = apply_ufunc
+
+
+def apply_ufunc(func, *args, input_core_dims=None, output_core_dims=None,  # pylint: disable=function-redefined
+                exclude_dims=None, **kwargs):
+  """Element-wise form, or ONE core dimension moved last and allowed to change
+  size (`exclude_dims`): what ZonalEnergySpectrum.compute asks for."""
+  if input_core_dims is None:
+    return _elementwise_apply_ufunc(func, *args, **kwargs)
+  (core,), = input_core_dims
+  (out_core,), = output_core_dims
+  assert exclude_dims == {core} and len(args) == 1 and not kwargs
+
+  def one(da):
+    if core not in da.dims:
+      return da
+    moved = da.transpose(*[d for d in da.dims if d != core], core)
+    data = np.asarray(func(np.asarray(moved.values)))
+    coords = {k: c for k, c in moved.coords.items() if core not in c.dims}
+    return DataArray(data, moved.dims[:-1] + (out_core,), coords, da.name,
+                     da.attrs)
+
+  obj = args[0]
+  return obj._map(one) if isinstance(obj, Dataset) else one(obj)  # pylint: disable=protected-access
+
+
+def _rename_dims(self, mapping):
+  if isinstance(self, Dataset):
+    out = Dataset(attrs=self.attrs)
+    out._coords = {k: _xl.Coord(tuple(mapping.get(d, d) for d in c.dims),  # pylint: disable=protected-access
+                                np.asarray(c.values)) for k, c in
+                   self.coords.items()}
+    for k in self.keys():
+      out[k] = _rename_dims(self[k], mapping)
+    return out
+  coords = {k: _xl.Coord(tuple(mapping.get(d, d) for d in c.dims), c.values)
+            for k, c in self.coords.items()}
+  return DataArray(self.data, tuple(mapping.get(d, d) for d in self.dims),
+                   coords, self.name, self.attrs)
+
+
+DataArray.rename_dims = _rename_dims
+Dataset.rename_dims = _rename_dims
+
+_lite_getattr = DataArray.__getattr__
+
+
+def _da_getattr(self, name):
+  try:
+    return _lite_getattr(self, name)
+  except AttributeError:
+    dims = self.__dict__.get('dims', ())
+    if name in dims:  # a dimension without coordinate reads as 0 .. n-1
+      return DataArray(np.arange(self.shape[dims.index(name)]), (name,),
+                       name=name)
+    raise
+
+
+DataArray.__getattr__ = _da_getattr
+
+
+def _da_setitem(self, key, value):
+  """da['coord'] = DataArray: (re)assigns a coordinate."""
+  self._set_coord(key, value)  # pylint: disable=protected-access
+
+
+DataArray.__setitem__ = _da_setitem
+_lite_da_init = DataArray.__init__
+
+
+def _da_init(self, data=None, coords=None, dims=None, name=None, attrs=None):
+  """xarray's argument order (data, coords, dims, name, attrs); `dims` may be
+  a single name; coordinates may be DataArrays."""
+  if isinstance(coords, (tuple, list, str)) and not isinstance(dims, dict) and (
+      dims is None or isinstance(dims, dict)):
+    coords, dims = dims, coords  # called the xarray_lite way (data, dims, coords)
+  if isinstance(dims, dict) and not isinstance(coords, dict):
+    coords, dims = dims, coords
+  _lite_da_init(self, data, dims, coords, name, attrs)
+
+
+DataArray.__init__ = _da_init
+
+
+def _da_argsort(self, axis=-1, **kw):
+  del kw
+  return self._replace(np.argsort(self.values, axis=axis))  # pylint: disable=protected-access
+
+
+DataArray.argsort = _da_argsort
+_lite_expand_dims = DataArray.expand_dims
+
+
+def _da_expand_dims(self, dim=None, axis=None, **kw):
+  out = _lite_expand_dims(self, dim, **kw) if axis in (None, 0) else None
+  if out is not None:
+    return out
+  out = _lite_expand_dims(self, dim, **kw)
+  new = [d for d in out.dims if d not in self.dims]
+  assert axis == -1
+  return out.transpose(*self.dims, *new)
+
+
+DataArray.expand_dims = _da_expand_dims
+
+
+_outer_concat = concat
+
+
+def _with_dim(obj, dim):
+  """An object that holds `dim` only as a scalar coordinate becomes length 1
+  along it (what xr.concat does before joining)."""
+  if isinstance(obj, Dataset):
+    out = Dataset(attrs=obj.attrs)
+    label = obj.coords[dim].values if dim in obj.coords else None
+    for k in obj.keys():
+      out[k] = _with_dim(obj[k].assign_coords({dim: label})
+                         if label is not None and dim not in obj[k].dims
+                         else obj[k], dim)
+    return out
+  if dim in obj.dims:
+    return obj
+  label = np.asarray(obj.coords[dim].values).reshape(1) if (
+      dim in obj.coords) else None
+  coords = {k: c for k, c in obj.coords.items() if k != dim}
+  if label is not None:
+    coords[dim] = _xl.Coord((dim,), label)
+  return DataArray(np.asarray(obj.values)[None], (dim,) + obj.dims, coords,
+                   obj.name, obj.attrs)
+
+
+def concat(objs, dim, **kwargs):  # pylint: disable=function-redefined
+  objs = list(objs)
+  if isinstance(dim, str) and any(
+      dim in (o.dims if isinstance(o, DataArray) else o.sizes) for o in objs):
+    objs = [_with_dim(o, dim) for o in objs]
+  return _outer_concat(objs, dim, **kwargs)
+
+
+class _GroupBy:
+  def __init__(self, obj, dim):
+    self.obj, self.dim = obj, dim
+
+  def apply(self, func):
+    n = self.obj.sizes[self.dim]
+    parts = [func(self.obj.isel({self.dim: slice(i, i + 1)})) for i in range(n)]
+    labels = self.obj.coords[self.dim].values
+    parts = [p.assign_coords({self.dim: labels[i]}) if self.dim not in p.dims
+             else p for i, p in enumerate(parts)]
+    return concat(parts, self.dim)
+
+  map = apply
+
+
+DataArray.groupby = lambda self, group, squeeze=True, **kw: _GroupBy(self, group)
+
+
+def _da_interp(self, coords=None, method='linear', **kw):
+  """1-D linear interpolation along ONE dimension coordinate; NaN outside the
+  coordinate's range (scipy.interpolate.interp1d, bounds_error=False)."""
+  assert method == 'linear'
+  (dim, new), = dict(coords or {}, **kw).items()
+  new = np.asarray(new, dtype=np.float64)
+  x = np.asarray(self.coords[dim].values, dtype=np.float64)
+  ax = self.dims.index(dim)
+  v = np.moveaxis(np.asarray(self.values, dtype=np.float64), ax, -1)
+  from scipy import interpolate
+  f = interpolate.interp1d(x, v, kind='linear', axis=-1, bounds_error=False,
+                           fill_value=np.nan, assume_sorted=False)
+  out = np.moveaxis(f(new), -1, ax)
+  c = {k: cc for k, cc in self.coords.items() if dim not in cc.dims}
+  c[dim] = _xl.Coord((dim,), new)
+  return DataArray(out, self.dims, c, self.name, self.attrs)
+
+
+DataArray.interp = _da_interp
+DataArray.__floordiv__ = lambda self, o: self._binary(o, np.floor_divide)  # pylint: disable=protected-access
+DataArray.__mod__ = lambda self, o: self._binary(o, np.mod)  # pylint: disable=protected-access

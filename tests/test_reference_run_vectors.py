@@ -28,7 +28,7 @@ import reference_cases as rc  # noqa: E402  pylint: disable=wrong-import-positio
 VECTORS = np.load(os.path.join(HERE, 'golden', 'reference_run_vectors.npz'))
 BY_CASE = {}
 for _key in VECTORS.files:
-  if _key.startswith('eval:'):  # evaluate_in_memory result files, see below
+  if _key.startswith(('eval:', 'extra:')):  # other call shapes, see below
     continue
   _cid, _var, _dims = _key.split('|')
   BY_CASE.setdefault(_cid, {})[_var] = (
@@ -287,3 +287,108 @@ def test_evaluate_in_memory_matches_the_reference_run(tmp_path):
   longitude, level and time selection / pressure-level suffixes / by-valid step
   thinning -- product on the stand-in context vs the reference's result files."""
   check_product_evaluations(fake_ctx.installed, tmp_path)
+
+
+# ------------------------------------------------------------------------------
+# Rank histogram + central reliability, SEEPS, zonal spectrum + interpolation,
+# wind speed
+# ------------------------------------------------------------------------------
+EXTRA_VECTORS = {}
+for _key in VECTORS.files:
+  if _key.startswith('extra:'):
+    _name, _, _dims = _key.split('|')
+    EXTRA_VECTORS[_name[6:]] = (tuple(d for d in _dims.split(',') if d),
+                                VECTORS[_key])
+
+EXTRA_TOL = {  # relative to the largest magnitude of the vector
+    'spectrum': 1e-5, 'spectrum_interp': 1e-5, 'seeps': 1e-5,
+    'spatial_seeps': 1e-5}
+
+
+def check_product_extras(scope):
+  from weatherbench2_b200 import (derived_variables, metrics,
+                                  xarray_lite as xl)
+  lib = types.SimpleNamespace(metrics=metrics,
+                              derived_variables=derived_variables)
+  with scope(), warnings.catch_warnings():
+    warnings.simplefilter('ignore', RuntimeWarning)
+    got = rc.run_extras(lib, xl.Dataset, rc.arrays())
+  assert set(got) == set(EXTRA_VECTORS) and len(got) == 12
+  for name, (dims, ref) in EXTRA_VECTORS.items():
+    gd, gv = got[name]
+    assert set(gd) == set(dims), (name, gd, dims)
+    gv = np.transpose(np.asarray(gv, dtype=np.float64),
+                      [gd.index(d) for d in dims])
+    np.testing.assert_array_equal(np.isnan(gv), np.isnan(ref), err_msg=name)
+    if name.startswith('rank_histogram'):
+      np.testing.assert_array_equal(gv, ref, err_msg=name)
+      continue
+    finite = np.isfinite(ref)
+    np.testing.assert_array_equal(gv[~finite & ~np.isnan(ref)],
+                                  ref[~finite & ~np.isnan(ref)], err_msg=name)
+    scale = np.abs(ref[finite]).max() if finite.any() else 1.0
+    tol = EXTRA_TOL.get(name.split('/')[0], 1e-6)
+    if '/' in name or name == 'wind_speed':  # coordinates, sqrt(u^2 + v^2)
+      np.testing.assert_allclose(gv[finite], ref[finite], rtol=1e-6, atol=0,
+                                 err_msg=name)
+    else:
+      assert np.abs(gv[finite] - ref[finite]).max() <= tol * scale, name
+
+
+def test_product_extras_match_the_reference_run():
+  """RankHistogram, central_reliability, SEEPS / SpatialSEEPS,
+  ZonalEnergySpectrum (+ its frequency / wavelength coordinates),
+  interpolate_spectral_frequencies and WindSpeed as the reference's own code
+  computed them."""
+  check_product_extras(fake_ctx.installed)
+
+
+def test_oracle_extras_match_the_reference_run():
+  x = rc.extra_inputs()
+  arr = rc.arrays()
+  f, t = arr['ens5/' + rc.Z], arr['truth/' + rc.Z]
+  for bins in (None, 3):
+    want_dims, want = EXTRA_VECTORS[f'rank_histogram/bins={bins}']
+    got, gd = orc.rank_histogram_one_hot(f, EDIMS, t, rc.DIMS, 'realization',
+                                         num_bins=bins)
+    np.testing.assert_array_equal(
+        np.transpose(got, [gd.index(d) for d in want_dims]), want)
+  # SEEPS
+  import pandas as pd
+  vt = x['init'][:, None] + x['lead'][None, :]
+  stamps = pd.DatetimeIndex(vt.ravel())
+  hour = (np.asarray(stamps.hour) // 12).reshape(vt.shape)
+  doy = (np.asarray(stamps.dayofyear) - 1).reshape(vt.shape)
+  wet = x['thr'][hour, doy]
+  p1 = x['dry'].mean(axis=(0, 1))
+  dims = ('init_time', 'lead_time', 'longitude', 'latitude')
+  point = orc.seeps_pointwise(x['pf'], x['pt'], wet, wet, p1)
+  got, gd = orc.spatial_average(point, dims, rc.LAT, rc.LON, None, True)
+  wd, want = EXTRA_VECTORS['seeps']
+  np.testing.assert_allclose(np.transpose(got, [gd.index(d) for d in wd]), want,
+                             rtol=2e-6)
+  point = orc.seeps_pointwise(x['pf'], x['pt'], wet, wet, p1, min_p1=0.3,
+                              max_p1=0.7)
+  wd, want = EXTRA_VECTORS['spatial_seeps']
+  np.testing.assert_allclose(np.transpose(point, [dims.index(d) for d in wd]),
+                             want, rtol=2e-6, equal_nan=True)
+  # zonal energy spectrum: values, frequency, wavelength
+  lon36 = np.linspace(0, 360, 36, endpoint=False)
+  sdims = ('time', 'level', 'latitude', 'longitude')
+  spec, sd, freq, wavelength = orc.zonal_energy_spectrum(
+      x['field'], sdims, rc.LAT, lon36)
+  wd, want = EXTRA_VECTORS['spectrum']
+  got = np.transpose(spec, [sd.index(d) for d in wd])
+  assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+  wd, want = EXTRA_VECTORS['spectrum/frequency']
+  got = freq if wd[0] == 'zonal_wavenumber' else freq.T
+  finite = np.isfinite(want)
+  np.testing.assert_array_equal(np.isfinite(got), finite)
+  np.testing.assert_allclose(got[finite], want[finite], rtol=1e-12)
+  wd, want = EXTRA_VECTORS['spectrum/wavelength']
+  got = wavelength if wd[0] == 'zonal_wavenumber' else wavelength.T
+  finite = np.isfinite(want)
+  np.testing.assert_allclose(got[finite], want[finite], rtol=1e-12)
+  fu, fv = x['field'], x['field'][::-1]
+  np.testing.assert_array_equal(np.sqrt(fu**2 + fv**2),
+                                EXTRA_VECTORS['wind_speed'][1])

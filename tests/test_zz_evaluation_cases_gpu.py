@@ -60,3 +60,7 @@ def test_cuda_operators_match_the_reference_run(case):
 def test_evaluate_in_memory_matches_the_reference_run_on_device(tmp_path):
   refrun.check_product_evaluations(contextlib.nullcontext, tmp_path, rtol=2e-5,
                                    atol=2e-6)
+
+
+def test_extras_match_the_reference_run_on_device():
+  refrun.check_product_extras(contextlib.nullcontext)

@@ -511,6 +511,11 @@ def _lookup(coord: np.ndarray, labels: np.ndarray, method=None) -> np.ndarray:
 def _broadcast(a: DataArray, b):
   """xarray arithmetic broadcasting: dims of `a`, then new dims of `b`."""
   av = a.values
+  if isinstance(b, (bool, int, float, complex)):
+    # a Python scalar stays "weak" (NEP 50): float32 data compared with /
+    # scaled by 0.25e-3 stays float32, as under xarray; np.asarray(scalar)
+    # would be a float64 0-d ARRAY and promote the whole operation
+    return av, b, a.dims, dict(a.coords)
   if not isinstance(b, DataArray):
     bv = _np(b)
     if bv.ndim not in (0,) and bv.shape != av.shape:
