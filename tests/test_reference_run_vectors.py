@@ -301,7 +301,7 @@ for _key in VECTORS.files:
                                 VECTORS[_key])
 
 EXTRA_TOL = {  # relative to the largest magnitude of the vector
-    'spectrum': 1e-5, 'spectrum_interp': 1e-5, 'seeps': 1e-5,
+    'spectrum': 1e-5, 'spectrum_interp': 2e-5, 'seeps': 1e-5,
     'spatial_seeps': 1e-5}
 
 
