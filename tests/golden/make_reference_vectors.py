@@ -28,7 +28,7 @@ sys.path[:0] = [ROOT, os.path.join(HERE, 'xarray_shim'), '/root/reference', HERE
 
 import xarray as xr  # noqa: E402  (the shim)
 from weatherbench2 import (config, derived_variables, evaluation, metrics,  # noqa: E402
-                           regions, thresholds)
+                           regions, regridding, thresholds)
 
 import reference_cases as rc  # noqa: E402
 import reference_eval_cases as rec  # noqa: E402
@@ -95,7 +95,8 @@ def main():
       warnings.simplefilter('ignore', RuntimeWarning)
       extras = rc.run_extras(
           types.SimpleNamespace(metrics=metrics,
-                                derived_variables=derived_variables),
+                                derived_variables=derived_variables,
+                                regridding=regridding),
           xr.Dataset, arr)
     for name, (dims, values) in extras.items():
       out[f"extra:{name}||{','.join(dims)}"] = values

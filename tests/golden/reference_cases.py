@@ -311,4 +311,51 @@ def run_extras(lib, Dataset, arr):  # pylint: disable=invalid-name
   put('spectrum_interp/frequency', interp['frequency'])
   put('wind_speed', lib.derived_variables.WindSpeed(
       u_name=U, v_name=V).compute(sds))
+  if hasattr(lib, 'regridding'):
+    out.update(run_regridders(lib.regridding, Dataset))
+  return out
+
+
+def run_regridders(rg, Dataset):  # pylint: disable=invalid-name
+  """The three regridders of weatherbench2/regridding.py on a field with a NaN
+  patch: global -> global, and source / target grids without poles or without
+  periodic longitudes (uncovered target cells come out NaN)."""
+  rs = np.random.RandomState(31337)
+  out = {}
+  fdims = ('field', 'longitude', 'latitude')
+  slon = np.linspace(0, 360, 24, endpoint=False)
+  slat = np.linspace(-90, 90, 13)
+  x = rs.standard_normal((3, 24, 13)).astype(np.float32)
+  x[1, 3:6, 4:7] = np.nan
+  x[2, :2, :] = np.nan  # across the longitude seam
+  tlon = np.linspace(0, 360, 10, endpoint=False)
+  tlat = np.linspace(-90, 90, 7)
+  grids = {
+      'global': (rg.Grid.from_degrees(slon, slat),
+                 rg.Grid.from_degrees(tlon, tlat)),
+      'no_poles': (rg.Grid(longitudes=slon, latitudes=slat[1:-1],
+                           periodic=True, includes_poles=False),
+                   rg.Grid(longitudes=tlon, latitudes=tlat, periodic=True,
+                           includes_poles=True)),
+      'limited_area': (rg.Grid(longitudes=slon[4:16], latitudes=slat[2:10],
+                               periodic=False, includes_poles=False),
+                       rg.Grid(longitudes=tlon[1:6], latitudes=tlat[1:5],
+                               periodic=False, includes_poles=False)),
+  }
+  crop = {'global': x, 'no_poles': x[:, :, 1:-1],
+          'limited_area': x[:, 4:16, 2:10]}
+  for gname, (source, target) in grids.items():
+    for cls in ('ConservativeRegridder', 'BilinearRegridder',
+                'NearestRegridder'):
+      r = getattr(rg, cls)(source, target)
+      out[f'regrid/{cls}/{gname}'] = (
+          fdims, np.asarray(r.regrid_array(crop[gname]), dtype=np.float32))
+  # regrid_dataset: dims (time, latitude, longitude), latitude decreasing
+  ds = Dataset({Z: (('time', 'latitude', 'longitude'),
+                    np.ascontiguousarray(np.transpose(x, (0, 2, 1))[:, ::-1]))},
+               dict(time=np.arange(3), latitude=slat[::-1], longitude=slon))
+  source, target = grids['global']
+  res = rg.ConservativeRegridder(source, target).regrid_dataset(ds)[Z]
+  out['regrid_dataset'] = (tuple(res.dims), np.asarray(res.values,
+                                                        dtype=np.float32))
   return out

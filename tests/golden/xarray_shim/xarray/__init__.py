@@ -472,20 +472,29 @@ def apply_ufunc(func, *args, input_core_dims=None, output_core_dims=None,  # pyl
                 exclude_dims=None, **kwargs):
   """Element-wise form, or ONE core dimension moved last and allowed to change
   size (`exclude_dims`): what ZonalEnergySpectrum.compute asks for."""
+  vectorize = kwargs.pop('vectorize', False)
   if input_core_dims is None:
     return _elementwise_apply_ufunc(func, *args, **kwargs)
-  (core,), = input_core_dims
-  (out_core,), = output_core_dims
-  assert exclude_dims == {core} and len(args) == 1 and not kwargs
+  core, = input_core_dims
+  out_core, = output_core_dims
+  core, out_core = tuple(core), tuple(out_core)
+  assert exclude_dims == set(core) and len(args) == 1 and not kwargs
 
   def one(da):
-    if core not in da.dims:
+    if not all(d in da.dims for d in core):
       return da
-    moved = da.transpose(*[d for d in da.dims if d != core], core)
-    data = np.asarray(func(np.asarray(moved.values)))
-    coords = {k: c for k, c in moved.coords.items() if core not in c.dims}
-    return DataArray(data, moved.dims[:-1] + (out_core,), coords, da.name,
-                     da.attrs)
+    lead = tuple(d for d in da.dims if d not in core)
+    moved = da.transpose(*lead, *core)
+    v = np.asarray(moved.values)
+    if vectorize:  # one call per slab, like np.vectorize with a signature
+      flat = v.reshape((-1,) + v.shape[len(lead):])
+      slabs = [np.asarray(func(flat[i])) for i in range(flat.shape[0])]
+      data = np.stack(slabs).reshape(v.shape[:len(lead)] + slabs[0].shape)
+    else:
+      data = np.asarray(func(v))
+    coords = {k: c for k, c in moved.coords.items()
+              if not any(d in core for d in c.dims)}
+    return DataArray(data, lead + out_core, coords, da.name, da.attrs)
 
   obj = args[0]
   return obj._map(one) if isinstance(obj, Dataset) else one(obj)  # pylint: disable=protected-access

@@ -306,14 +306,15 @@ EXTRA_TOL = {  # relative to the largest magnitude of the vector
 
 
 def check_product_extras(scope):
-  from weatherbench2_b200 import (derived_variables, metrics,
+  from weatherbench2_b200 import (derived_variables, metrics, regridding,
                                   xarray_lite as xl)
   lib = types.SimpleNamespace(metrics=metrics,
-                              derived_variables=derived_variables)
+                              derived_variables=derived_variables,
+                              regridding=regridding)
   with scope(), warnings.catch_warnings():
     warnings.simplefilter('ignore', RuntimeWarning)
     got = rc.run_extras(lib, xl.Dataset, rc.arrays())
-  assert set(got) == set(EXTRA_VECTORS) and len(got) == 12
+  assert set(got) == set(EXTRA_VECTORS) and len(got) == 22
   for name, (dims, ref) in EXTRA_VECTORS.items():
     gd, gv = got[name]
     assert set(gd) == set(dims), (name, gd, dims)
@@ -327,7 +328,11 @@ def check_product_extras(scope):
     np.testing.assert_array_equal(gv[~finite & ~np.isnan(ref)],
                                   ref[~finite & ~np.isnan(ref)], err_msg=name)
     tol = EXTRA_TOL.get(name.split('/')[0], 1e-6)
-    if '/' in name or name == 'wind_speed':  # coordinates, sqrt(u^2 + v^2)
+    if name.startswith('regrid'):
+      # float32 contraction (the reference: JAX einsum; here NumPy stands in)
+      np.testing.assert_allclose(gv[finite], ref[finite], rtol=1e-5, atol=2e-6,
+                                 err_msg=name)
+    elif '/' in name or name == 'wind_speed':  # coordinates, sqrt(u^2 + v^2)
       np.testing.assert_allclose(gv[finite], ref[finite], rtol=1e-6, atol=0,
                                  err_msg=name)
     elif name.startswith('spectrum'):
@@ -400,3 +405,36 @@ def test_oracle_extras_match_the_reference_run():
   fu, fv = x['field'], x['field'][::-1]
   np.testing.assert_array_equal(np.sqrt(fu**2 + fv**2),
                                 EXTRA_VECTORS['wind_speed'][1])
+
+
+def test_oracle_regridders_match_the_reference_run():
+  """weatherbench2/regridding.py's own ConservativeRegridder / Bilinear /
+  Nearest (run on a NumPy stand-in for jax.numpy) against the oracle."""
+  rs = np.random.RandomState(31337)
+  slon = np.linspace(0, 360, 24, endpoint=False)
+  slat = np.linspace(-90, 90, 13)
+  x = rs.standard_normal((3, 24, 13)).astype(np.float32)
+  x[1, 3:6, 4:7] = np.nan
+  x[2, :2, :] = np.nan
+  tlon = np.linspace(0, 360, 10, endpoint=False)
+  tlat = np.linspace(-90, 90, 7)
+  grids = {
+      'global': (orc.Grid(slon, slat), orc.Grid(tlon, tlat), x),
+      'no_poles': (orc.Grid(slon, slat[1:-1], includes_poles=False),
+                   orc.Grid(tlon, tlat), x[:, :, 1:-1]),
+      'limited_area': (orc.Grid(slon[4:16], slat[2:10], periodic=False,
+                                includes_poles=False),
+                       orc.Grid(tlon[1:6], tlat[1:5], periodic=False,
+                                includes_poles=False), x[:, 4:16, 2:10]),
+  }
+  fns = {'ConservativeRegridder': orc.conservative_regrid,
+         'BilinearRegridder': orc.bilinear_regrid,
+         'NearestRegridder': orc.nearest_regrid}
+  for gname, (source, target, field) in grids.items():
+    for cls, fn in fns.items():
+      _, want = EXTRA_VECTORS[f'regrid/{cls}/{gname}']
+      got = fn(field, source, target)
+      np.testing.assert_array_equal(np.isnan(got), np.isnan(want),
+                                    err_msg=f'{cls}/{gname}')
+      np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6,
+                                 equal_nan=True, err_msg=f'{cls}/{gname}')
