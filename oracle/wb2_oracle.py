@@ -8,13 +8,19 @@ The product package (``weatherbench2_b200``) never imports anything from
 ``oracle/``; its numerical path is the CUDA library behind the C ABI in
 ``include/wb2b200.h`` and it fails loudly when that library is missing.
 
-Parity status: **pinned** against every known-answer value the reference's own
-tests hold for this path (``tests/test_oracle_golden.py`` lists them with the
-reference test file:line).  The reference itself cannot be imported in this
-container or on the GPU box (it needs xarray / jax / apache_beam, none of which
-are installed and there is no network), so the oracle restates, operation for
-operation, what xarray (>=2024.11), NumPy (>=2.1) and JAX do underneath the
-reference's calls.  Each function cites the reference lines it follows
+Parity status: **pinned** (1) against every known-answer value the reference's
+own tests hold for this path (``tests/test_oracle_golden.py`` lists them with
+the reference test file:line) and (2) against vectors produced by EXECUTING the
+reference's own modules in the build container
+(``tests/golden/make_reference_vectors.py`` -> ``reference_run_vectors.npz``,
+checked by ``tests/test_reference_run_vectors.py``): metrics.py, regions.py,
+thresholds.py, derived_variables.py, regridding.py and evaluation.py, imported
+from /root/reference and run on stand-ins for the libraries that cannot be
+installed there (xarray -> a re-implemented subset, jax.numpy -> NumPy with
+32-bit results, apache_beam / xarray_beam -> import stubs).  Those vectors pin
+the REFERENCE logic restated here; what xarray (>=2024.11), NumPy (>=2.1) and
+JAX do underneath the reference's calls remains restated, operation for
+operation, both in that stand-in and -- independently -- in this module.  Each function cites the reference lines it follows
 (paths relative to ``/root/reference``).
 
 Everything works on plain ``numpy`` arrays plus a tuple of dimension names
