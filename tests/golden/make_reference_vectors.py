@@ -96,7 +96,7 @@ def main():
       extras = rc.run_extras(
           types.SimpleNamespace(metrics=metrics,
                                 derived_variables=derived_variables,
-                                regridding=regridding),
+                                regridding=regridding, regions=regions),
           xr.Dataset, arr)
     for name, (dims, values) in extras.items():
       out[f"extra:{name}||{','.join(dims)}"] = values

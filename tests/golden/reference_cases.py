@@ -313,6 +313,46 @@ def run_extras(lib, Dataset, arr):  # pylint: disable=invalid-name
       u_name=U, v_name=V).compute(sds))
   if hasattr(lib, 'regridding'):
     out.update(run_regridders(lib.regridding, Dataset))
+  if hasattr(lib, 'regions'):
+    out.update(run_region_index_sets(lib.regions, Dataset))
+  return out
+
+
+REGION_SLICES = {
+    'tropics': dict(lat=[(-20, 20)]),
+    'extra_tropics': dict(lat=[(None, -20), (20, None)]),
+    'europe_wrap': dict(lat=[(35, 75)], lon=[(360 - 12.5, None), (0, 42.5)]),
+    'on_grid_points': dict(lat=[(-30, 60)], lon=[(30, 200)]),
+    'between_points': dict(lat=[(-27.3, 61.2)], lon=[(33.3, 196.1)]),
+    'overlapping': dict(lat=[(-30, 10), (0, 40)]),  # duplicates are kept
+    'single_point': dict(lat=[(0, 0)], lon=[(180, 180)]),
+    'reversed_bounds': dict(lat=[(20, -20)]),       # selects nothing
+    'outside': dict(lon=[(400, 500)]),              # selects nothing
+}
+
+
+def run_region_index_sets(regions, Dataset):  # pylint: disable=invalid-name
+  """SliceRegion.apply (regions.py:57-98) on a 10-degree grid: which rows /
+  columns each label slice selects (both ends inclusive, list-of-slices
+  concatenated without de-duplication), as coordinate labels and weights."""
+  lat = np.linspace(-90, 90, 19)
+  lon = np.linspace(0, 360, 36, endpoint=False)
+  data = np.arange(19 * 36, dtype=np.float32).reshape(19, 36)
+  ds = Dataset({Z: (('latitude', 'longitude'), data)},
+               dict(latitude=lat, longitude=lon))
+  weights = ds[Z] * 0 + 1
+  out = {}
+  for name, spec in REGION_SLICES.items():
+    region = regions.SliceRegion(lat_slice=_slices(spec.get('lat')),
+                                 lon_slice=_slices(spec.get('lon')))
+    sub, w = region.apply(ds, weights)
+    out[f'region/{name}/latitude'] = (('latitude',),
+                                      np.asarray(sub['latitude'].values))
+    out[f'region/{name}/longitude'] = (('longitude',),
+                                       np.asarray(sub['longitude'].values))
+    out[f'region/{name}/data'] = (tuple(sub[Z].dims),
+                                  np.asarray(sub[Z].values))
+    out[f'region/{name}/weights'] = (tuple(w.dims), np.asarray(w.values))
   return out
 
 

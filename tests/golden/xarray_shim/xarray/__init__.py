@@ -295,6 +295,17 @@ def _da_sel(self, indexers=None, method=None, drop=False, tolerance=None,
         rest[d] = slice(stamp(v.start, False), stamp(v.stop, True))
       elif isinstance(v, str):
         rest[d] = slice(stamp(v, False), stamp(v, True))
+  for d, v in list(rest.items()):
+    # label slices go through pandas itself (Index.slice_indexer is what
+    # xarray calls): both ends inclusive, bounds need not be labels
+    if isinstance(v, slice) and d in out.coords:
+      index = pd.Index(np.asarray(out.coords[d].values))
+      if index.is_monotonic_increasing or index.is_monotonic_decreasing:
+        plain = lambda b: (np.asarray(b.values)[()]  # noqa: E731
+                           if isinstance(b, DataArray) else b)
+        positions = index.slice_indexer(plain(v.start), plain(v.stop), v.step)
+        out = out.isel({d: positions})
+        del rest[d]
   if rest:
     if tolerance is not None:
       for d, v in rest.items():

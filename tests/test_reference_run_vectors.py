@@ -306,15 +306,15 @@ EXTRA_TOL = {  # relative to the largest magnitude of the vector
 
 
 def check_product_extras(scope):
-  from weatherbench2_b200 import (derived_variables, metrics, regridding,
-                                  xarray_lite as xl)
+  from weatherbench2_b200 import (derived_variables, metrics, regions,
+                                  regridding, xarray_lite as xl)
   lib = types.SimpleNamespace(metrics=metrics,
                               derived_variables=derived_variables,
-                              regridding=regridding)
+                              regridding=regridding, regions=regions)
   with scope(), warnings.catch_warnings():
     warnings.simplefilter('ignore', RuntimeWarning)
     got = rc.run_extras(lib, xl.Dataset, rc.arrays())
-  assert set(got) == set(EXTRA_VECTORS) and len(got) == 22
+  assert set(got) == set(EXTRA_VECTORS) and len(got) == 58
   for name, (dims, ref) in EXTRA_VECTORS.items():
     gd, gv = got[name]
     assert set(gd) == set(dims), (name, gd, dims)
@@ -328,6 +328,10 @@ def check_product_extras(scope):
     np.testing.assert_array_equal(gv[~finite & ~np.isnan(ref)],
                                   ref[~finite & ~np.isnan(ref)], err_msg=name)
     tol = EXTRA_TOL.get(name.split('/')[0], 1e-6)
+    if name.startswith('region/'):  # index sets: exact
+      assert gv.shape == ref.shape, (name, gv.shape, ref.shape)
+      np.testing.assert_array_equal(gv, ref, err_msg=name)
+      continue
     if name.startswith('regrid'):
       # float32 contraction (the reference: JAX einsum; here NumPy stands in)
       np.testing.assert_allclose(gv[finite], ref[finite], rtol=1e-5, atol=2e-6,
@@ -438,3 +442,29 @@ def test_oracle_regridders_match_the_reference_run():
                                     err_msg=f'{cls}/{gname}')
       np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6,
                                  equal_nan=True, err_msg=f'{cls}/{gname}')
+
+
+def test_oracle_region_index_sets_match_the_reference_run():
+  """regions.py's SliceRegion.apply, run by the reference itself with pandas'
+  own `Index.slice_indexer` underneath, against the oracle's restatement of the
+  label-slice rule (both ends inclusive, list-of-slices concatenated without
+  de-duplication, reversed or outside bounds select nothing)."""
+  lat = np.linspace(-90, 90, 19)
+  lon = np.linspace(0, 360, 36, endpoint=False)
+  data = np.arange(19 * 36, dtype=np.float32).reshape(19, 36)
+  for name, spec in rc.REGION_SLICES.items():
+    region = orc.SliceRegion(lat_slice=rc._slices(spec.get('lat')),  # pylint: disable=protected-access
+                             lon_slice=rc._slices(spec.get('lon')))  # pylint: disable=protected-access
+    x, w, rlat, rlon = orc._region_apply(region, data, np.ones_like(data),  # pylint: disable=protected-access
+                                         lat, lon)
+    np.testing.assert_array_equal(
+        rlat, EXTRA_VECTORS[f'region/{name}/latitude'][1], err_msg=name)
+    np.testing.assert_array_equal(
+        rlon, EXTRA_VECTORS[f'region/{name}/longitude'][1], err_msg=name)
+    np.testing.assert_array_equal(x, EXTRA_VECTORS[f'region/{name}/data'][1],
+                                  err_msg=name)
+    np.testing.assert_array_equal(w,
+                                  EXTRA_VECTORS[f'region/{name}/weights'][1],
+                                  err_msg=name)
+  assert EXTRA_VECTORS['region/overlapping/latitude'][1].size == 10  # 5 + 5
+  assert EXTRA_VECTORS['region/reversed_bounds/latitude'][1].size == 0
