@@ -10,16 +10,9 @@ layer end to end, against the expectations the reference's authors wrote.
 
 Needs the reference checkout (/root/reference, read-only, build container
 only): skipped elsewhere.  Nothing is copied from it."""
-import os
-import re
-import subprocess
-import sys
-
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REFERENCE = '/root/reference'
-GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+import reference_suite_runner as runner
 
 # the four allowed failures are derived variables this repository does not
 # build (off the hot path): precipitation accumulation, relative humidity
@@ -34,26 +27,12 @@ SUITES = [
 ]
 
 
-@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'weatherbench2')),
+@pytest.mark.skipif(not runner.available(),
                     reason='the reference checkout is only in the build '
                     'container')
 @pytest.mark.parametrize('name,n_pass,may_fail', SUITES,
                          ids=[s[0] for s in SUITES])
-def test_reference_own_tests_pass_against_the_product(name, n_pass, may_fail,
-                                                      tmp_path):
-  env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1',
-             PYTHONPATH=os.pathsep.join([
-                 ROOT, os.path.join(ROOT, 'tests'),
-                 os.path.join(GOLDEN, 'product_as_reference'),
-                 os.path.join(GOLDEN, 'xarray_shim')]))
-  run = subprocess.run(
-      [sys.executable, '-m', 'pytest',
-       os.path.join(REFERENCE, 'weatherbench2', name), '-q', '-p',
-       'no:cacheprovider', '-p', 'standin_context_plugin'],
-      cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900,
-      check=False)
-  out = run.stdout + run.stderr
-  failed = re.findall(r'^FAILED \S+::(\w+)', out, re.M)
-  passed = int((re.search(r'(\d+) passed', out) or [0, 0])[1])
-  assert sorted(failed) == sorted(may_fail), out[-3000:]
-  assert passed == n_pass, out[-2000:]
+def test_reference_own_tests_pass_against_the_product(name, n_pass, may_fail):
+  passed, failed, tail = runner.result('product', name)
+  assert failed == sorted(may_fail), tail
+  assert passed == n_pass, tail
