@@ -31,3 +31,11 @@ for _name in ('schema', 'utils', 'test_utils'):
   sys.modules[f'weatherbench2.{_name}'] = _mod
   _spec.loader.exec_module(_mod)
   globals()[_name] = _mod
+
+if os.environ.get('WB2_STANDIN_CONTEXT') == '1':
+  # a test file run with `python file.py` (absltest.main) instead of pytest:
+  # no plugin hook, so the NumPy stand-in context is installed here for good
+  import fake_ctx  # pylint: disable=wrong-import-position
+  from weatherbench2_b200 import _lib as _wb2_lib  # pylint: disable=wrong-import-position
+  _STANDIN = fake_ctx.FakeContext()
+  _wb2_lib.default_context = lambda device=None: _STANDIN

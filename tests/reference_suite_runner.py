@@ -43,6 +43,34 @@ def _start_all():
            'no:cacheprovider'] + spec['plugins'],
           cwd=tmp, env=env, stdout=log, stderr=subprocess.STDOUT)
       _running[(config, name)] = (proc, log)
+  _start_evaluation_test(tmp)
+
+
+def _start_evaluation_test(tmp):
+  """evaluation_test.py needs absltest's own runner (create_tempdir): run it
+  with `python file.py`; the alias package installs the stand-in context."""
+  spec = CONFIGS['product']
+  env = dict(os.environ, PYTHONDONTWRITEBYTECODE='1', WB2_STANDIN_CONTEXT='1',
+             PYTHONPATH=os.pathsep.join(spec['path']), TEST_TMPDIR=tmp)
+  log = open(os.path.join(tmp, 'product.evaluation_test.py.log'), 'w+')
+  proc = subprocess.Popen(
+      [sys.executable, os.path.join(REFERENCE, 'weatherbench2',
+                                    'evaluation_test.py')],
+      cwd=tmp, env=env, stdout=log, stderr=subprocess.STDOUT)
+  _running[('product', 'evaluation_test.py')] = (proc, log)
+
+
+def absltest_result(config: str, name: str):
+  """(number of tests run, ok?, tail of the output) of a `python file.py` run."""
+  if not _running:
+    _start_all()
+  proc, log = _running[(config, name)]
+  proc.wait(timeout=1200)
+  log.seek(0)
+  out = log.read()
+  ran = int((re.search(r'^Ran (\d+) test', out, re.M) or [0, 0])[1])
+  ok = proc.returncode == 0 and re.search(r'^OK', out, re.M) is not None
+  return ran, ok, out[-3000:]
 
 
 def result(config: str, name: str):

@@ -36,3 +36,15 @@ def test_reference_own_tests_pass_against_the_product(name, n_pass, may_fail):
   passed, failed, tail = runner.result('product', name)
   assert failed == sorted(may_fail), tail
   assert passed == n_pass, tail
+
+
+@pytest.mark.skipif(not runner.available(),
+                    reason='the reference checkout is only in the build '
+                    'container')
+def test_reference_evaluation_consistency_test_passes_against_the_product():
+  """weatherbench2/evaluation_test.py (test_in_memory_and_beam_consistency):
+  zarr-path configs -> `evaluate_in_memory` and `evaluate_with_beam(...,
+  runner='DirectRunner')` of THIS repository write the same result files (the
+  stand-in xarray keeps "zarr stores" and "netCDF files" in memory / pickles)."""
+  ran, ok, tail = runner.absltest_result('product', 'evaluation_test.py')
+  assert ok and ran == 1, tail
